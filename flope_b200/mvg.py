@@ -1,0 +1,62 @@
+"""Host-side box logic and yaw nullification, mirroring sunflower/utils/mvg.py.
+
+Same names, argument meaning and return types as the reference:
+  squarify_bb            sunflower/utils/mvg.py:324-343
+  bb_in_frame            sunflower/utils/mvg.py:345-351
+  filter_very_large_bb   sunflower/utils/mvg.py:354-362
+  nullify_yaw_batch      sunflower/utils/mvg.py:240-251
+``squarify_filter_batch`` is the vectorised form used by the predictors; it calls
+the C-ABI ``flope_squarify_filter`` (integer, bit-exact with the scalar pair).
+"""
+import numpy as np
+
+
+def squarify_bb(bb):
+    xmin, ymin, xmax, ymax = bb
+    xrange_ = xmax - xmin
+    yrange_ = ymax - ymin
+    diff = abs(xrange_ - yrange_)
+    if diff % 2 == 0:
+        decrease_min = increase_max = diff / 2
+    else:
+        decrease_min = (diff + 1) / 2
+        increase_max = (diff - 1) / 2
+    if xrange_ > yrange_:
+        ymin -= decrease_min
+        ymax += increase_max
+    elif xrange_ < yrange_:
+        xmin -= decrease_min
+        xmax += increase_max
+    return [int(xmin), int(ymin), int(xmax), int(ymax)]
+
+
+def bb_in_frame(bb, img_shape):
+    h, w = img_shape[0], img_shape[1]
+    xmin, ymin, xmax, ymax = bb
+    if xmin < 0 or ymin < 0 or xmax > w or ymax > h:
+        return False
+    return True
+
+
+def filter_very_large_bb(bb_dino):
+    bb_dino = np.array(bb_dino)
+    x_range = bb_dino[:, 2] - bb_dino[:, 0]
+    y_range = bb_dino[:, 3] - bb_dino[:, 1]
+    area = x_range * y_range
+    large_area = area > 5 * np.median(area)
+    return bb_dino[np.logical_not(large_area)]
+
+
+def squarify_filter_batch(boxes, img_shape):
+    """(N,4) integer xyxy -> (square boxes (M,4) int32, keep (N,) bool) through the C-ABI."""
+    from . import _lib
+    boxes = np.ascontiguousarray(np.asarray(boxes).reshape(-1, 4), dtype=np.int32)
+    return _lib.squarify_filter(boxes, int(img_shape[0]), int(img_shape[1]))
+
+
+def nullify_yaw_batch(rotmat):
+    """Euler 'zyx' -> zero the z angle -> recompose; float64 (N,3,3), same SciPy calls as the reference."""
+    from scipy.spatial.transform import Rotation as sciR
+    e = sciR.from_matrix(np.asarray(rotmat)).as_euler('zyx', degrees=True)
+    e[:, 0] = 0.0
+    return sciR.from_euler('zyx', e, degrees=True).as_matrix()
