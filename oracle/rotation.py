@@ -69,8 +69,8 @@ def assemble_rt(rot, xyz=None):
 
 
 def geodesic_deg(Ra, Rb):
-    """Angle of Ra^T Rb in degrees, per sample."""
+    """Angle of Ra^T Rb in degrees, per sample (chordal form: well conditioned near 0)."""
     Ra = np.asarray(Ra, dtype=np.float64)
     Rb = np.asarray(Rb, dtype=np.float64)
-    tr = np.einsum('nij,nij->n', Ra, Rb)
-    return np.degrees(np.arccos(np.clip((tr - 1.0) / 2.0, -1.0, 1.0)))
+    chord = np.linalg.norm((Ra - Rb).reshape(-1, 9), axis=1)          # = 2*sqrt(2)*sin(theta/2)
+    return np.degrees(2.0 * np.arcsin(np.clip(chord / (2.0 * np.sqrt(2.0)), 0.0, 1.0)))
