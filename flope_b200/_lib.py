@@ -1,0 +1,203 @@
+"""ctypes binding of libflope_b200.so (include/flope_b200.h) - the only way Python reaches the kernels.
+
+PyTorch is used for device memory and streams only: tensors are passed as raw device
+pointers and the current CUDA stream handle.  There is no fallback: if the library is
+missing or a call fails, FlopeError is raised.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libflope_b200.so")
+
+INTERP_LINEAR, INTERP_LANCZOS4 = 0, 1
+OUT_F32_NCHW, OUT_ENGINE = 0, 1
+
+SYMBOLS = [
+    "flope_version", "flope_last_error", "flope_engine_create", "flope_engine_destroy",
+    "flope_engine_load_weights", "flope_squarify_filter", "flope_roi_crop", "flope_posenet_forward",
+    "flope_pose_head", "flope_nullify_yaw", "flope_infer_frames", "flope_engine_last_launches",
+    "flope_debug_activation", "flope_debug_normalise_lut", "flope_debug_set",
+]
+
+
+class FlopeError(RuntimeError):
+    pass
+
+
+class TensorDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int), ("shape", C.c_int64 * 4)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FlopeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.flope_last_error.restype = C.c_char_p
+        L.flope_engine_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
+        L.flope_engine_destroy.argtypes = [C.c_void_p]
+        L.flope_engine_destroy.restype = None
+        L.flope_engine_load_weights.argtypes = [C.c_void_p, C.POINTER(TensorDesc), C.c_int]
+        L.flope_squarify_filter.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.flope_roi_crop.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.flope_posenet_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.flope_pose_head.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.flope_nullify_yaw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.flope_infer_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.flope_engine_last_launches.argtypes = [C.c_void_p]
+        L.flope_debug_activation.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.flope_debug_activation.restype = C.c_int64
+        L.flope_debug_normalise_lut.argtypes = [C.c_void_p, C.c_void_p]
+        L.flope_debug_set.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc < 0:
+        raise FlopeError(f"flope_b200 error {rc}: {lib().flope_last_error().decode()}")
+    return rc
+
+
+def squarify_filter(boxes_i32, H, W):
+    """(N,4) int32 -> (kept square boxes (M,4) int32, keep (N,) bool).  Host function of the C ABI."""
+    n = boxes_i32.shape[0]
+    sq = np.zeros((n, 4), np.int32)
+    keep = np.zeros((n,), np.uint8)
+    check(lib().flope_squarify_filter(boxes_i32.ctypes.data, n, H, W, sq.ctypes.data, keep.ctypes.data))
+    keep = keep.astype(bool)
+    return sq[keep], keep
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Engine:
+    """Owns one flope_engine (weights + workspace) on one CUDA device."""
+
+    def __init__(self, device=0, max_batch=256, crop_hw=224):
+        import torch
+        if not torch.cuda.is_available():
+            raise FlopeError("flope_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = int(device)
+        self.max_batch = int(max_batch)
+        self.crop_hw = int(crop_hw)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().flope_engine_create(C.byref(self._h), self.device, self.max_batch, self.crop_hw))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().flope_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights ------------------------------------------------------------------
+    def load_state_dict(self, state_dict):
+        """Takes the reference PoseResNet.state_dict() (torch tensors or numpy arrays)."""
+        keep, descs = [], []
+        for k, v in state_dict.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            a = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            keep.append((k.encode(), a))
+        arr = (TensorDesc * len(keep))()
+        for i, (name, a) in enumerate(keep):
+            arr[i].name = name
+            arr[i].data = a.ctypes.data
+            arr[i].ndim = a.ndim
+            for d in range(a.ndim):
+                arr[i].shape[d] = a.shape[d]
+        check(lib().flope_engine_load_weights(self._h, arr, len(keep)))
+
+    # -- kernels ------------------------------------------------------------------
+    def roi_crop(self, frames, masks, boxes5, S, interp, out=None, out_fmt=OUT_F32_NCHW):
+        import torch
+        n = boxes5.shape[0]
+        n_frames, H, W, _ = frames.shape
+        if out_fmt == OUT_F32_NCHW and out is None:
+            out = torch.empty((n, 3, S, S), dtype=torch.float32, device=frames.device)
+        check(lib().flope_roi_crop(self._h, _ptr(frames), n_frames, H, W, frames.stride(0), _ptr(masks), _ptr(boxes5), n, S,
+                                   interp, _ptr(out), out_fmt, _stream()))
+        return out
+
+    def posenet_forward(self, x, n=None, out=None):
+        """x: (n,3,S,S) float32 cuda tensor, or None to consume crops written by roi_crop(OUT_ENGINE)."""
+        import torch
+        if x is not None:
+            n = x.shape[0]
+        if out is None:
+            out = torch.empty((n, 9), dtype=torch.float32, device=f"cuda:{self.device}")
+        check(lib().flope_posenet_forward(self._h, _ptr(x), n, _ptr(out), _stream()))
+        return out
+
+    def pose_head(self, r9, want_yaw=True):
+        import torch
+        n = r9.shape[0]
+        R = torch.empty((n, 3, 3), dtype=torch.float32, device=r9.device)
+        Ry = torch.empty((n, 3, 3), dtype=torch.float64, device=r9.device) if want_yaw else None
+        check(lib().flope_pose_head(self._h, _ptr(r9), n, _ptr(R), _ptr(Ry), _stream()))
+        return R, Ry
+
+    def nullify_yaw(self, R):
+        import torch
+        n = R.shape[0]
+        Ry = torch.empty((n, 3, 3), dtype=torch.float64, device=R.device)
+        check(lib().flope_nullify_yaw(self._h, _ptr(R), n, _ptr(Ry), _stream()))
+        return Ry
+
+    def infer_frames(self, frames, masks, boxes5, interp, want_r9=False, want_R=True, want_yaw=True, out=None):
+        import torch
+        n = boxes5.shape[0]
+        n_frames, H, W, _ = frames.shape
+        dev = frames.device
+        r9 = torch.empty((n, 9), dtype=torch.float32, device=dev) if want_r9 else None
+        R = torch.empty((n, 3, 3), dtype=torch.float32, device=dev) if want_R else None
+        Ry = (out if out is not None else torch.empty((n, 3, 3), dtype=torch.float64, device=dev)) if want_yaw else None
+        check(lib().flope_infer_frames(self._h, _ptr(frames), n_frames, H, W, frames.stride(0), _ptr(masks), _ptr(boxes5), n,
+                                       interp, _ptr(r9), _ptr(R), _ptr(Ry), _stream()))
+        return r9, R, Ry
+
+    def last_launches(self):
+        return int(lib().flope_engine_last_launches(self._h))
+
+    # -- test hooks ---------------------------------------------------------------
+    def debug_activation(self, name, n):
+        import torch
+        # generous upper bound, then trim to the size the library reports
+        S = self.crop_hw
+        buf = torch.empty((n * 64 * (S // 2) * (S // 2),), dtype=torch.float32, device=f"cuda:{self.device}")
+        chw = check(lib().flope_debug_activation(self._h, name.encode(), n, _ptr(buf), _stream()))
+        return buf[: n * chw], chw
+
+    def debug_set(self, key, value):
+        check(lib().flope_debug_set(self._h, key.encode(), int(value)))
+
+
+def debug_normalise_lut(device=0):
+    import torch
+    out = torch.empty((256, 256), dtype=torch.float32, device=f"cuda:{device}")
+    check(lib().flope_debug_normalise_lut(_ptr(out), _stream()))
+    return out

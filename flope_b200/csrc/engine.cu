@@ -1,0 +1,711 @@
+// flope_b200: engine + C ABI (include/flope_b200.h) for the B200-native FloPE pose path.
+//
+// Host side only orchestrates: it owns the blocked-pixel activation buffers, folds
+// BatchNorm, packs weights into UMMA-ready tiles and launches the sm_100a kernels of
+// roi_crop.cuh / conv_igemm.cuh / pointwise.cuh / pose_head.cuh on the caller's stream.
+// There is no CPU compute path: without a CUDA device every entry point fails loudly.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/flope_b200.h"
+#include "conv_igemm.cuh"
+#include "pointwise.cuh"
+#include "pose_head.cuh"
+#include "roi_crop.cuh"
+
+using namespace flope;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(x)                                                                           \
+  do {                                                                                        \
+    cudaError_t _e = (x);                                                                     \
+    if (_e != cudaSuccess) return fail(FLOPE_ECUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr int kMaxSmem = 232448;      // 227 KB opt-in dynamic shared memory per CTA
+constexpr int kTwoCtaSmem = 113 * 1024;  // budget that lets two CTAs share one SM
+constexpr int kMaxTM = 1024;
+
+long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+Geom make_geom(int C, int H, int W, int pad, int max_batch) {
+  Geom g;
+  g.C = C; g.H = H; g.W = W; g.Hp = H + pad; g.Wp = W + pad;
+  g.base = (int)round_up(2 * g.Wp + 8, 8);
+  const long long npos = (long long)max_batch * g.Hp * g.Wp;
+  g.plane = g.base + round_up(npos, 1024) + kMaxTM + round_up(2 * g.Wp + 8, 8);
+  return g;
+}
+
+struct ActBuf {
+  Geom g{};
+  __nv_bfloat16* d = nullptr;
+  int planes = 0;
+  bool parity = false;
+  size_t bytes() const { return (size_t)planes * g.plane * 8 * sizeof(__nv_bfloat16); }
+};
+
+enum ConvKind { K_CONV3 = 0, K_CONV3_S2 = 1, K_DOWN1_S2 = 2, K_STEM = 3, K_FC = 4 };
+
+struct TapDef { int r, s; };
+
+struct ConvLayer {
+  std::string name, wkey, bnkey, biaskey;
+  ConvKind kind;
+  int cin, cout;
+  int in_buf, out_buf, res_buf;
+  int relu;
+  int out_mode;
+  // derived
+  int n_tile = 64, mt = 4;
+  size_t smem = 0;
+  ConvParams p{};
+  std::vector<std::vector<TapDef>> group_taps;   // per group: (r,s) of each weight tile, for packing
+  std::vector<int> group_cin;                    // first input channel of each group
+  __nv_bfloat16* d_w = nullptr;
+  float* d_scale = nullptr;
+  float* d_bias = nullptr;
+};
+
+template <int N_TILE, int MT>
+cudaError_t conv_set_attr() {
+  return cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+}
+template <int N_TILE, int MT>
+void conv_launch_t(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  conv_igemm_kernel<N_TILE, MT><<<grid, kConvThreads, smem, st>>>(p);
+}
+
+#define FOR_EACH_CONV_CFG(X) X(64, 1) X(64, 2) X(64, 4) X(64, 8) X(128, 1) X(128, 2) X(128, 4)
+
+cudaError_t conv_set_all_attrs() {
+  cudaError_t e;
+#define X(N, M) if ((e = conv_set_attr<N, M>()) != cudaSuccess) return e;
+  FOR_EACH_CONV_CFG(X)
+#undef X
+  return cudaSuccess;
+}
+bool conv_launch(int n_tile, int mt, const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+#define X(N, M) if (n_tile == N && mt == M) { conv_launch_t<N, M>(p, grid, smem, st); return true; }
+  FOR_EACH_CONV_CFG(X)
+#undef X
+  return false;
+}
+
+}  // namespace
+
+struct flope_engine {
+  int device = 0, max_batch = 0, S = 0;
+  bool weights_loaded = false;
+  int dbg_swap = 0;
+  int launches = 0;
+  std::vector<ActBuf> bufs;
+  std::map<std::string, int> act_names;          // debug name -> buffer index
+  std::vector<ConvLayer> layers;
+  int buf_x0 = -1, buf_stem = -1, buf_pool_in = -1, buf_pool = -1, buf_mp_out = -1;
+  float* d_feat = nullptr;                       // (max_batch, 2048) fp32
+  float* d_wrot = nullptr;                       // (9, 2048) fp32
+  float* d_brot = nullptr;                       // (9,)
+  float* d_r9 = nullptr;                         // (max_batch, 9) scratch
+  int feat_dim = 2048;
+};
+
+namespace {
+
+int add_buf(flope_engine* e, int C, int H, int W, int pad, bool parity, const char* dbg_name) {
+  ActBuf b;
+  b.g = make_geom(C, H, W, pad, e->max_batch);
+  b.parity = parity;
+  b.planes = (C / 8) * (parity ? 4 : 1);
+  e->bufs.push_back(b);
+  const int idx = (int)e->bufs.size() - 1;
+  if (dbg_name) e->act_names[dbg_name] = idx;
+  return idx;
+}
+
+void add_conv(flope_engine* e, const std::string& name, ConvKind kind, int cin, int cout, int in_buf, int out_buf,
+              int res_buf, int relu, int out_mode, const std::string& wkey, const std::string& bnkey,
+              const std::string& biaskey = "") {
+  ConvLayer L;
+  L.name = name; L.kind = kind; L.cin = cin; L.cout = cout;
+  L.in_buf = in_buf; L.out_buf = out_buf; L.res_buf = res_buf;
+  L.relu = relu; L.out_mode = out_mode;
+  L.wkey = wkey; L.bnkey = bnkey; L.biaskey = biaskey;
+  e->layers.push_back(L);
+}
+
+// Fill the group/tap tables and pick the tile configuration of one layer.
+int plan_conv(flope_engine* e, ConvLayer& L) {
+  const ActBuf& in = e->bufs[L.in_buf];
+  ConvParams& p = L.p;
+  std::memset(&p, 0, sizeof(p));
+  const int Wp = in.g.Wp;
+  p.in = in.d;
+  p.in_plane = in.g.plane;
+  p.in_base = in.g.base;
+  p.Hp = in.g.Hp; p.Wp = in.g.Wp; p.H = in.g.H; p.W = in.g.W;
+  L.group_taps.clear();
+  L.group_cin.clear();
+  int ntap_entries = 0;
+  auto add_tap_entry = [&](int shift) { p.tap_shift[ntap_entries] = shift; return ntap_entries++; };
+  switch (L.kind) {
+    case K_CONV3: {
+      p.kc8 = 8;
+      p.n_groups = L.cin / 64;
+      for (int t = 0; t < 9; ++t) add_tap_entry((t / 3 - 1) * Wp + (t % 3 - 1));
+      for (int g = 0; g < p.n_groups; ++g) {
+        p.group_plane[g] = g * 8; p.group_tapofs[g] = 0; p.group_ntaps[g] = 9;
+        std::vector<TapDef> td;
+        for (int t = 0; t < 9; ++t) td.push_back({t / 3, t % 3});
+        L.group_taps.push_back(td);
+        L.group_cin.push_back(g * 64);
+      }
+      p.halo_before = Wp + 1; p.halo_after = Wp + 1;
+      break;
+    }
+    case K_CONV3_S2: {   // input is parity-split; its Geom is the half-resolution (= output) grid
+      p.kc8 = 8;
+      const int nch = L.cin / 64;
+      p.n_groups = 4 * nch;
+      int ofs[4], cnt[4];
+      std::vector<TapDef> tds[4];
+      for (int q = 0; q < 4; ++q) {
+        const int ph = q >> 1, pw = q & 1;
+        ofs[q] = ntap_entries; cnt[q] = 0;
+        for (int r = 0; r < 3; ++r) {
+          if (((r + 1) & 1) != ph) continue;          // input row 2i+r-1 has parity (r+1)&1
+          for (int s = 0; s < 3; ++s) {
+            if (((s + 1) & 1) != pw) continue;
+            add_tap_entry((r == 0 ? -1 : 0) * Wp + (s == 0 ? -1 : 0));
+            tds[q].push_back({r, s});
+            ++cnt[q];
+          }
+        }
+      }
+      for (int q = 0; q < 4; ++q)
+        for (int c = 0; c < nch; ++c) {
+          const int g = q * nch + c;
+          p.group_plane[g] = q * (L.cin / 8) + c * 8;
+          p.group_tapofs[g] = ofs[q]; p.group_ntaps[g] = cnt[q];
+          L.group_taps.push_back(tds[q]);
+          L.group_cin.push_back(c * 64);
+        }
+      p.halo_before = Wp + 1; p.halo_after = 0;
+      break;
+    }
+    case K_DOWN1_S2: {
+      p.kc8 = 8;
+      p.n_groups = L.cin / 64;
+      add_tap_entry(0);
+      for (int g = 0; g < p.n_groups; ++g) {
+        p.group_plane[g] = g * 8; p.group_tapofs[g] = 0; p.group_ntaps[g] = 1;   // parity (0,0) planes come first
+        L.group_taps.push_back({{1, 1}});   // the 1x1 kernel is stored as (0,0); handled in the packer
+        L.group_cin.push_back(g * 64);
+      }
+      p.halo_before = 0; p.halo_after = 0;
+      break;
+    }
+    case K_STEM: {
+      p.kc8 = 2;
+      p.n_groups = 1;
+      std::vector<TapDef> td;
+      for (int t = 0; t < 16; ++t) {
+        add_tap_entry((t / 4 - 2) * Wp + (t % 4 - 2));
+        td.push_back({t / 4, t % 4});
+      }
+      p.group_plane[0] = 0; p.group_tapofs[0] = 0; p.group_ntaps[0] = 16;
+      L.group_taps.push_back(td);
+      L.group_cin.push_back(0);
+      p.halo_before = 2 * Wp + 2; p.halo_after = Wp + 1;
+      break;
+    }
+    case K_FC: {
+      p.kc8 = 8;
+      p.n_groups = L.cin / 64;
+      add_tap_entry(0);
+      for (int g = 0; g < p.n_groups; ++g) {
+        p.group_plane[g] = g * 8; p.group_tapofs[g] = 0; p.group_ntaps[g] = 1;
+        L.group_taps.push_back({{0, 0}});
+        L.group_cin.push_back(g * 64);
+      }
+      p.halo_before = 0; p.halo_after = 0;
+      break;
+    }
+  }
+  if (p.n_groups > kMaxGroups || ntap_entries > kMaxTaps) return fail(FLOPE_EINVAL, "conv plan exceeds table sizes");
+  p.taps_total = 0;
+  for (int g = 0; g < p.n_groups; ++g) p.taps_total += p.group_ntaps[g];
+
+  // ---- output side ----
+  p.relu = L.relu;
+  p.out_mode = L.out_mode;
+  p.Cout = L.cout;
+  if (L.out_mode == OUT_F32_ROWS) {
+    p.out = e->d_feat;
+  } else {
+    const ActBuf& ob = e->bufs[L.out_buf];
+    p.out = ob.d;
+    p.out_plane = ob.g.plane; p.out_base = ob.g.base; p.out_Hp = ob.g.Hp; p.out_Wp = ob.g.Wp;
+  }
+  if (L.res_buf >= 0) {
+    const ActBuf& rb = e->bufs[L.res_buf];
+    p.res = rb.d;
+    p.res_plane = rb.g.plane; p.res_base = rb.g.base; p.res_Hp = rb.g.Hp; p.res_Wp = rb.g.Wp;
+  }
+
+  // ---- tile configuration ----
+  L.n_tile = L.cout >= 128 ? 128 : 64;
+  L.mt = 256 / L.n_tile;                       // 256 TMEM columns -> two CTAs can share an SM
+  const int halo = p.halo_before + p.halo_after;
+  auto smem_of = [&](int n_a, int n_b) {
+    return (size_t)1024 + (size_t)n_a * p.kc8 * (L.mt * 128 + halo) * 16 + (size_t)n_b * p.kc8 * L.n_tile * 16 +
+           2 * L.n_tile * sizeof(float);
+  };
+  int best_a = 0, best_b = 0;
+  for (int budget : {kTwoCtaSmem, kMaxSmem}) {
+    for (int n_b : {4, 3, 2}) {
+      const int nb = std::min(n_b, p.taps_total);
+      int n_a = std::min(p.n_groups, 4);
+      while (n_a >= 1 && smem_of(n_a, nb) > (size_t)budget) --n_a;
+      if (n_a >= 1) { best_a = n_a; best_b = nb; break; }
+    }
+    if (best_a) break;
+  }
+  if (!best_a) return fail(FLOPE_EINVAL, "conv layer " + L.name + " does not fit in shared memory");
+  p.n_a_slots = best_a; p.n_b_slots = best_b;
+  L.smem = smem_of(best_a, best_b);
+  return FLOPE_OK;
+}
+
+int build_network(flope_engine* e) {
+  const int S = e->S;
+  const int s2 = S / 2, s4 = S / 4;
+  e->buf_x0 = add_buf(e, 16, s2, s2, 2, false, nullptr);
+  e->buf_stem = add_buf(e, 64, s2, s2, 1, false, "stem");
+  int cur = add_buf(e, 64, s4, s4, 1, false, "maxpool");
+  e->buf_mp_out = cur;
+  add_conv(e, "conv1", K_STEM, 16, 64, e->buf_x0, e->buf_stem, -1, 1, OUT_PLAIN, "base.conv1.weight", "base.bn1");
+  int C = 64, side = s4;
+  for (int stage = 1; stage <= 4; ++stage) {
+    const std::string ln = "base.layer" + std::to_string(stage);
+    const std::string dn = "layer" + std::to_string(stage);
+    int bufB = add_buf(e, C, side, side, 1, false, nullptr);
+    int blk0_out;
+    if (stage == 1) {
+      blk0_out = add_buf(e, C, side, side, 1, false, (dn + ".0").c_str());
+      add_conv(e, dn + ".0.conv1", K_CONV3, C, C, cur, bufB, -1, 1, OUT_PLAIN, ln + ".0.conv1.weight", ln + ".0.bn1");
+      add_conv(e, dn + ".0.conv2", K_CONV3, C, C, bufB, blk0_out, cur, 1, OUT_PLAIN, ln + ".0.conv2.weight", ln + ".0.bn2");
+    } else {
+      // `cur` is the parity-split output of the previous stage, geometry = this stage's grid
+      const int cin = C / 2;
+      int bufD = add_buf(e, C, side, side, 1, false, nullptr);
+      blk0_out = add_buf(e, C, side, side, 1, false, (dn + ".0").c_str());
+      add_conv(e, dn + ".0.conv1", K_CONV3_S2, cin, C, cur, bufB, -1, 1, OUT_PLAIN, ln + ".0.conv1.weight", ln + ".0.bn1");
+      add_conv(e, dn + ".0.downsample", K_DOWN1_S2, cin, C, cur, bufD, -1, 0, OUT_PLAIN, ln + ".0.downsample.0.weight",
+               ln + ".0.downsample.1");
+      add_conv(e, dn + ".0.conv2", K_CONV3, C, C, bufB, blk0_out, bufD, 1, OUT_PLAIN, ln + ".0.conv2.weight", ln + ".0.bn2");
+    }
+    int blk1_out;
+    int mode;
+    if (stage < 4) {
+      blk1_out = add_buf(e, C, side / 2, side / 2, 1, true, (dn + ".1").c_str());
+      mode = OUT_PARITY;
+    } else {
+      blk1_out = add_buf(e, C, side, side, 1, false, (dn + ".1").c_str());
+      mode = OUT_PLAIN;
+    }
+    add_conv(e, dn + ".1.conv1", K_CONV3, C, C, blk0_out, bufB, -1, 1, OUT_PLAIN, ln + ".1.conv1.weight", ln + ".1.bn1");
+    add_conv(e, dn + ".1.conv2", K_CONV3, C, C, bufB, blk1_out, blk0_out, 1, mode, ln + ".1.conv2.weight", ln + ".1.bn2");
+    cur = blk1_out;
+    if (stage < 4) { C *= 2; side /= 2; }
+  }
+  e->buf_pool_in = cur;
+  e->buf_pool = add_buf(e, 512, 1, 1, 0, false, nullptr);
+  add_conv(e, "fc", K_FC, 512, e->feat_dim, e->buf_pool, -1, -1, 1, OUT_F32_ROWS, "base.fc.0.weight", "", "base.fc.0.bias");
+  return FLOPE_OK;
+}
+
+void pack_weights_host(const ConvLayer& L, const float* w, std::vector<__nv_bfloat16>& out) {
+  const ConvParams& p = L.p;
+  const int NT = L.n_tile;
+  const int n_tiles = L.cout / NT;
+  const size_t tile_elems = (size_t)p.kc8 * NT * 8;
+  out.assign((size_t)n_tiles * p.taps_total * tile_elems, __float2bfloat16_rn(0.f));
+  for (int nt = 0; nt < n_tiles; ++nt) {
+    size_t tile = (size_t)nt * p.taps_total;
+    for (int g = 0; g < p.n_groups; ++g) {
+      for (size_t t = 0; t < L.group_taps[g].size(); ++t, ++tile) {
+        const TapDef td = L.group_taps[g][t];
+        __nv_bfloat16* dst = out.data() + tile * tile_elems;
+        for (int k8 = 0; k8 < p.kc8; ++k8)
+          for (int n = 0; n < NT; ++n)
+            for (int j = 0; j < 8; ++j) {
+              const int co = nt * NT + n;
+              float v = 0.f;
+              switch (L.kind) {
+                case K_CONV3:
+                case K_CONV3_S2: {
+                  const int ci = L.group_cin[g] + k8 * 8 + j;
+                  v = w[(((size_t)co * L.cin + ci) * 3 + td.r) * 3 + td.s];
+                  break;
+                }
+                case K_DOWN1_S2:
+                case K_FC: {
+                  const int ci = L.group_cin[g] + k8 * 8 + j;
+                  v = w[(size_t)co * L.cin + ci];
+                  break;
+                }
+                case K_STEM: {
+                  // k = by*8 + bx*4 + c ; w8 = 7x7 kernel zero-padded to 8x8 at the top/left
+                  const int by = k8, bx = j >> 2, c = j & 3;
+                  const int i8 = 2 * td.r + by, j8 = 2 * td.s + bx;
+                  if (c < 3 && i8 >= 1 && j8 >= 1) v = w[(((size_t)co * 3 + c) * 7 + (i8 - 1)) * 7 + (j8 - 1)];
+                  break;
+                }
+              }
+              dst[((size_t)k8 * NT + n) * 8 + j] = __float2bfloat16_rn(v);
+            }
+      }
+    }
+  }
+}
+
+int run_conv(flope_engine* e, ConvLayer& L, int n, cudaStream_t st) {
+  ConvParams p = L.p;
+  p.n_positions = (long long)n * p.Hp * p.Wp;
+  p.wgt = L.d_w; p.scale = L.d_scale; p.bias = L.d_bias;
+  p.dbg_swap_lbo_sbo = e->dbg_swap;
+  const int TM = L.mt * 128;
+  dim3 grid((unsigned)((p.n_positions + TM - 1) / TM), (unsigned)(L.cout / L.n_tile));
+  if (!conv_launch(L.n_tile, L.mt, p, grid, L.smem, st)) return fail(FLOPE_EINVAL, "no kernel instance for " + L.name);
+  ++e->launches;
+  return FLOPE_OK;
+}
+
+int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  return (int)std::min<long long>(std::max<long long>(g, 1), 148LL * 16);
+}
+
+// Backbone + fc on the stem input already present in buf_x0; leaves features in d_feat.
+int run_backbone(flope_engine* e, int n, cudaStream_t st) {
+  int rc;
+  size_t li = 0;
+  if ((rc = run_conv(e, e->layers[li++], n, st))) return rc;       // stem
+  {
+    const ActBuf& a = e->bufs[e->buf_stem];
+    const ActBuf& b = e->bufs[e->buf_mp_out];
+    const long long total = (long long)(a.g.C / 8) * n * b.g.H * b.g.W;
+    maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(a.d, a.g, b.d, b.g, n);
+    ++e->launches;
+  }
+  for (; li + 1 < e->layers.size(); ++li)
+    if ((rc = run_conv(e, e->layers[li], n, st))) return rc;
+  {
+    const ActBuf& a = e->bufs[e->buf_pool_in];
+    const ActBuf& b = e->bufs[e->buf_pool];
+    const int total = (a.g.C / 8) * n;
+    avgpool_kernel<<<(total + 127) / 128, 128, 0, st>>>(a.d, a.g, b.d, b.g, n);
+    ++e->launches;
+  }
+  if ((rc = run_conv(e, e->layers[li], n, st))) return rc;         // fc
+  CUDA_TRY(cudaGetLastError());
+  return FLOPE_OK;
+}
+
+int run_head(flope_engine* e, const float* feat, const float* r9_in, const float* R_in, int n, float* r9_out,
+             float* R_out, double* Ryaw_out, cudaStream_t st) {
+  const int warps_per_block = 4;
+  pose_head_kernel<<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+      feat, e->feat_dim, e->d_wrot, e->d_brot, r9_in, n, r9_out, R_out, Ryaw_out, R_in);
+  ++e->launches;
+  CUDA_TRY(cudaGetLastError());
+  return FLOPE_OK;
+}
+
+int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W, int64_t frame_stride,
+            const uint8_t* d_masks, const int32_t* d_boxes, int n, int S, int interp, void* d_out, int out_fmt,
+            cudaStream_t st) {
+  (void)n_frames;
+  RoiParams rp{};
+  rp.frames = d_frames; rp.frame_stride = frame_stride; rp.masks = d_masks; rp.mask_stride = (long long)H * W;
+  rp.H = H; rp.W = W; rp.boxes = d_boxes; rp.n = n; rp.S = S; rp.out_fmt = out_fmt;
+  if (out_fmt == FLOPE_OUT_ENGINE) {
+    rp.out = e->bufs[e->buf_x0].d;
+    rp.g = e->bufs[e->buf_x0].g;
+  } else {
+    rp.out = d_out;
+  }
+  rp.rows_per_strip = S >= 448 ? 128 : 112;
+  const int block = S >= 256 ? 256 : ((S + 31) / 32 * 32);
+  dim3 grid((S + block - 1) / block, (S + rp.rows_per_strip - 1) / rp.rows_per_strip, n);
+  const bool has_mask = d_masks != nullptr;
+  if (interp == FLOPE_INTERP_LANCZOS4) {
+    if (has_mask) roi_crop_kernel<8, true><<<grid, block, 0, st>>>(rp);
+    else roi_crop_kernel<8, false><<<grid, block, 0, st>>>(rp);
+  } else {
+    if (has_mask) roi_crop_kernel<2, true><<<grid, block, 0, st>>>(rp);
+    else roi_crop_kernel<2, false><<<grid, block, 0, st>>>(rp);
+  }
+  ++e->launches;
+  CUDA_TRY(cudaGetLastError());
+  return FLOPE_OK;
+}
+
+__global__ void normalise_lut_kernel(float* out) {
+  const int i = threadIdx.x, m = blockIdx.x;
+  out[m * 256 + i] = __fdiv_rn((float)(i * m), 65025.f);
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int flope_version(void) { return 100; }
+const char* flope_last_error(void) { return g_err.c_str(); }
+
+int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_hw) {
+  if (!out) return fail(FLOPE_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (max_batch < 1 || crop_hw < 32 || crop_hw % 32 != 0 || crop_hw > 1024)
+    return fail(FLOPE_EINVAL, "max_batch must be >= 1 and crop_hw a multiple of 32 in [32,1024]");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(FLOPE_EINVAL, "no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(FLOPE_ECUDA, "flope_b200 kernels are built for sm_100a (B200) only");
+  CUDA_TRY(conv_set_all_attrs());
+  flope_engine* e = new flope_engine();
+  e->device = device; e->max_batch = max_batch; e->S = crop_hw;
+  int rc = build_network(e);
+  if (rc) { delete e; return rc; }
+  for (ActBuf& b : e->bufs) {
+    if (cudaMalloc(&b.d, b.bytes()) != cudaSuccess) { flope_engine_destroy(e); return fail(FLOPE_ENOMEM, "activation buffer allocation failed"); }
+    CUDA_TRY(cudaMemset(b.d, 0, b.bytes()));
+  }
+  CUDA_TRY(cudaMalloc(&e->d_feat, (size_t)(e->max_batch + kMaxTM) * e->feat_dim * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&e->d_wrot, (size_t)9 * e->feat_dim * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&e->d_brot, 9 * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&e->d_r9, (size_t)e->max_batch * 9 * sizeof(float)));
+  for (ConvLayer& L : e->layers)
+    if ((rc = plan_conv(e, L))) { flope_engine_destroy(e); return rc; }
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = e;
+  return FLOPE_OK;
+}
+
+void flope_engine_destroy(flope_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  for (ActBuf& b : e->bufs) cudaFree(b.d);
+  for (ConvLayer& L : e->layers) { cudaFree(L.d_w); cudaFree(L.d_scale); cudaFree(L.d_bias); }
+  cudaFree(e->d_feat); cudaFree(e->d_wrot); cudaFree(e->d_brot); cudaFree(e->d_r9);
+  delete e;
+}
+
+int flope_engine_load_weights(flope_engine* e, const flope_tensor_desc* tensors, int n) {
+  if (!e || !tensors) return fail(FLOPE_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  std::map<std::string, const flope_tensor_desc*> sd;
+  for (int i = 0; i < n; ++i)
+    if (tensors[i].name && tensors[i].data) sd[tensors[i].name] = &tensors[i];
+  auto need = [&](const std::string& k, int64_t numel) -> const float* {
+    auto it = sd.find(k);
+    if (it == sd.end()) return nullptr;
+    int64_t ne = 1;
+    for (int d = 0; d < it->second->ndim; ++d) ne *= it->second->shape[d];
+    return ne == numel ? it->second->data : nullptr;
+  };
+  for (ConvLayer& L : e->layers) {
+    int64_t wn = 0;
+    switch (L.kind) {
+      case K_CONV3: case K_CONV3_S2: wn = (int64_t)L.cout * L.cin * 9; break;
+      case K_DOWN1_S2: case K_FC: wn = (int64_t)L.cout * L.cin; break;
+      case K_STEM: wn = (int64_t)L.cout * 3 * 49; break;
+    }
+    const float* w = need(L.wkey, wn);
+    if (!w) return fail(FLOPE_EINVAL, "state_dict entry missing or mis-shaped: " + L.wkey);
+    std::vector<float> scale(L.cout, 1.f), bias(L.cout, 0.f);
+    if (!L.bnkey.empty()) {
+      const float* gw = need(L.bnkey + ".weight", L.cout);
+      const float* gb = need(L.bnkey + ".bias", L.cout);
+      const float* mu = need(L.bnkey + ".running_mean", L.cout);
+      const float* var = need(L.bnkey + ".running_var", L.cout);
+      if (!gw || !gb || !mu || !var) return fail(FLOPE_EINVAL, "BatchNorm entries missing for " + L.bnkey);
+      for (int c = 0; c < L.cout; ++c) {     // eval-mode fold, eps = 1e-5 (torchvision BatchNorm2d default)
+        const float s = gw[c] / std::sqrt(var[c] + 1e-5f);
+        scale[c] = s;
+        bias[c] = gb[c] - mu[c] * s;
+      }
+    } else {
+      const float* b = need(L.biaskey, L.cout);
+      if (!b) return fail(FLOPE_EINVAL, "bias missing: " + L.biaskey);
+      for (int c = 0; c < L.cout; ++c) bias[c] = b[c];
+    }
+    std::vector<__nv_bfloat16> packed;
+    pack_weights_host(L, w, packed);
+    cudaFree(L.d_w); cudaFree(L.d_scale); cudaFree(L.d_bias);
+    L.d_w = nullptr; L.d_scale = nullptr; L.d_bias = nullptr;
+    CUDA_TRY(cudaMalloc(&L.d_w, packed.size() * sizeof(__nv_bfloat16)));
+    CUDA_TRY(cudaMalloc(&L.d_scale, L.cout * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&L.d_bias, L.cout * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(L.d_w, packed.data(), packed.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(L.d_scale, scale.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(L.d_bias, bias.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  const float* wr = need("fc_rot.weight", (int64_t)9 * e->feat_dim);
+  const float* br = need("fc_rot.bias", 9);
+  if (!wr || !br) return fail(FLOPE_EINVAL, "fc_rot entries missing");
+  CUDA_TRY(cudaMemcpy(e->d_wrot, wr, (size_t)9 * e->feat_dim * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(e->d_brot, br, 9 * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaDeviceSynchronize());
+  e->weights_loaded = true;
+  return FLOPE_OK;
+}
+
+int flope_squarify_filter(const int32_t* boxes, int n, int H, int W, int32_t* out_sq, uint8_t* keep) {
+  if (n < 0 || (n > 0 && (!boxes || !out_sq || !keep))) return fail(FLOPE_EINVAL, "NULL argument");
+  for (int i = 0; i < n; ++i) {
+    // squarify_bb (mvg.py:324-343) on integers: the short side grows by diff, the extra pixel of an
+    // odd diff going to the min side; int() truncation is exact because every operand is integral
+    int64_t xmin = boxes[4 * i], ymin = boxes[4 * i + 1], xmax = boxes[4 * i + 2], ymax = boxes[4 * i + 3];
+    const int64_t xr = xmax - xmin, yr = ymax - ymin;
+    const int64_t diff = xr > yr ? xr - yr : yr - xr;
+    const int64_t lo = (diff % 2 == 0) ? diff / 2 : (diff + 1) / 2;
+    const int64_t hi = (diff % 2 == 0) ? diff / 2 : (diff - 1) / 2;
+    if (xr > yr) { ymin -= lo; ymax += hi; }
+    else if (xr < yr) { xmin -= lo; xmax += hi; }
+    out_sq[4 * i] = (int32_t)xmin; out_sq[4 * i + 1] = (int32_t)ymin;
+    out_sq[4 * i + 2] = (int32_t)xmax; out_sq[4 * i + 3] = (int32_t)ymax;
+    keep[i] = !(xmin < 0 || ymin < 0 || xmax > W || ymax > H);   // bb_in_frame (mvg.py:345-351)
+  }
+  return FLOPE_OK;
+}
+
+int flope_roi_crop(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W, int64_t frame_stride,
+                   const uint8_t* d_masks, const int32_t* d_boxes, int n, int S, int interp, void* d_out, int out_fmt,
+                   void* stream) {
+  if (!e || !d_frames || !d_boxes) return fail(FLOPE_EINVAL, "NULL argument");
+  if (n == 0) return FLOPE_OK;
+  if (n < 0 || S < 2 || S % 2) return fail(FLOPE_EINVAL, "bad n or S");
+  if (interp != FLOPE_INTERP_LINEAR && interp != FLOPE_INTERP_LANCZOS4) return fail(FLOPE_EINVAL, "bad interp");
+  if (out_fmt == FLOPE_OUT_ENGINE) {
+    if (S != e->S || n > e->max_batch) return fail(FLOPE_EINVAL, "engine-format crops need S == crop_hw and n <= max_batch");
+  } else if (out_fmt != FLOPE_OUT_F32_NCHW || !d_out) {
+    return fail(FLOPE_EINVAL, "bad out_fmt / d_out");
+  }
+  CUDA_TRY(cudaSetDevice(e->device));
+  e->launches = 0;
+  return run_roi(e, d_frames, n_frames, H, W, frame_stride, d_masks, d_boxes, n, S, interp, d_out, out_fmt,
+                 (cudaStream_t)stream);
+}
+
+int flope_posenet_forward(flope_engine* e, const float* d_in, int n, float* d_r9, void* stream) {
+  if (!e || !d_r9) return fail(FLOPE_EINVAL, "NULL argument");
+  if (!e->weights_loaded) return fail(FLOPE_ESTATE, "weights not loaded");
+  if (n == 0) return FLOPE_OK;
+  if (n < 0 || (!d_in && n > e->max_batch)) return fail(FLOPE_EINVAL, "bad n");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  e->launches = 0;
+  for (int done = 0; done < n; done += e->max_batch) {
+    const int nb = std::min(e->max_batch, n - done);
+    if (d_in) {
+      const ActBuf& x0 = e->bufs[e->buf_x0];
+      const long long total = (long long)nb * e->S * e->S;
+      ingest_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, st>>>(d_in + (size_t)done * 3 * e->S * e->S, nb, e->S, x0.d, x0.g);
+      ++e->launches;
+    }
+    int rc = run_backbone(e, nb, st);
+    if (rc) return rc;
+    if ((rc = run_head(e, e->d_feat, nullptr, nullptr, nb, d_r9 + (size_t)done * 9, nullptr, nullptr, st))) return rc;
+  }
+  return FLOPE_OK;
+}
+
+int flope_pose_head(flope_engine* e, const float* d_r9, int n, float* d_R, double* d_R_yaw, void* stream) {
+  if (!e || !d_r9) return fail(FLOPE_EINVAL, "NULL argument");
+  if (n == 0) return FLOPE_OK;
+  CUDA_TRY(cudaSetDevice(e->device));
+  e->launches = 0;
+  return run_head(e, nullptr, d_r9, nullptr, n, nullptr, d_R, d_R_yaw, (cudaStream_t)stream);
+}
+
+int flope_nullify_yaw(flope_engine* e, const float* d_R_in, int n, double* d_R_yaw, void* stream) {
+  if (!e || !d_R_in || !d_R_yaw) return fail(FLOPE_EINVAL, "NULL argument");
+  if (n == 0) return FLOPE_OK;
+  CUDA_TRY(cudaSetDevice(e->device));
+  e->launches = 0;
+  return run_head(e, nullptr, nullptr, d_R_in, n, nullptr, nullptr, d_R_yaw, (cudaStream_t)stream);
+}
+
+int flope_infer_frames(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W, int64_t frame_stride,
+                       const uint8_t* d_masks, const int32_t* d_boxes, int n, int interp, float* d_r9, float* d_R,
+                       double* d_R_yaw, void* stream) {
+  if (!e || !d_frames || !d_boxes) return fail(FLOPE_EINVAL, "NULL argument");
+  if (!e->weights_loaded) return fail(FLOPE_ESTATE, "weights not loaded");
+  if (n == 0) return FLOPE_OK;
+  if (n < 0) return fail(FLOPE_EINVAL, "bad n");
+  if (interp != FLOPE_INTERP_LINEAR && interp != FLOPE_INTERP_LANCZOS4) return fail(FLOPE_EINVAL, "bad interp");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  e->launches = 0;
+  for (int done = 0; done < n; done += e->max_batch) {
+    const int nb = std::min(e->max_batch, n - done);
+    int rc = run_roi(e, d_frames, n_frames, H, W, frame_stride, d_masks, d_boxes + (size_t)done * 5, nb, e->S, interp,
+                     nullptr, FLOPE_OUT_ENGINE, st);
+    if (rc) return rc;
+    if ((rc = run_backbone(e, nb, st))) return rc;
+    if ((rc = run_head(e, e->d_feat, nullptr, nullptr, nb, d_r9 ? d_r9 + (size_t)done * 9 : nullptr,
+                       d_R ? d_R + (size_t)done * 9 : nullptr, d_R_yaw ? d_R_yaw + (size_t)done * 9 : nullptr, st)))
+      return rc;
+  }
+  return FLOPE_OK;
+}
+
+int flope_engine_last_launches(const flope_engine* e) { return e ? e->launches : 0; }
+
+int64_t flope_debug_activation(flope_engine* e, const char* name, int n, float* d_out, void* stream) {
+  if (!e || !name || !d_out) return fail(FLOPE_EINVAL, "NULL argument");
+  auto it = e->act_names.find(name);
+  if (it == e->act_names.end()) return fail(FLOPE_EINVAL, std::string("unknown activation ") + name);
+  const ActBuf& b = e->bufs[it->second];
+  const int H = b.parity ? 2 * b.g.H : b.g.H, W = b.parity ? 2 * b.g.W : b.g.W;
+  const long long total = (long long)n * b.g.C * H * W;
+  unpack_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(b.d, b.g, b.parity ? 1 : 0, n, d_out);
+  if (cudaGetLastError() != cudaSuccess) return fail(FLOPE_ECUDA, "unpack launch failed");
+  return (int64_t)b.g.C * H * W;
+}
+
+int flope_debug_normalise_lut(float* d_out, void* stream) {
+  if (!d_out) return fail(FLOPE_EINVAL, "NULL argument");
+  normalise_lut_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(d_out);
+  CUDA_TRY(cudaGetLastError());
+  return FLOPE_OK;
+}
+
+int flope_debug_set(flope_engine* e, const char* key, int value) {
+  if (!e || !key) return fail(FLOPE_EINVAL, "NULL argument");
+  if (!std::strcmp(key, "swap_lbo_sbo")) { e->dbg_swap = value; return FLOPE_OK; }
+  return fail(FLOPE_EINVAL, std::string("unknown debug key ") + key);
+}
+
+}  // extern "C"

@@ -55,8 +55,12 @@ def squarify_filter_batch(boxes, img_shape):
 
 
 def nullify_yaw_batch(rotmat):
-    """Euler 'zyx' -> zero the z angle -> recompose; float64 (N,3,3), same SciPy calls as the reference."""
-    from scipy.spatial.transform import Rotation as sciR
-    e = sciR.from_matrix(np.asarray(rotmat)).as_euler('zyx', degrees=True)
-    e[:, 0] = 0.0
-    return sciR.from_euler('zyx', e, degrees=True).as_matrix()
+    """(N,3,3) rotations (numpy) -> float64 (N,3,3) with the 'zyx' yaw angle zeroed.
+
+    Same contract as the reference; computed by the fused pose-head kernel in fp64
+    (R' = Rx(gamma) Ry(beta), the closed form of SciPy's as_euler/from_euler round trip).
+    """
+    import torch
+    from .conversion import nullify_yaw_batch_cuda
+    r = torch.as_tensor(np.asarray(rotmat, dtype=np.float32)).cuda()
+    return nullify_yaw_batch_cuda(r).cpu().numpy()

@@ -1,0 +1,136 @@
+"""Drop-in predictors mirroring sunflower/predictor/{fast_pose_predictor,pose_predictor}.py.
+
+Same class names, constructor keywords and ``get_flower_poses(rgb, depth) -> (N,4,4) float64
+| None`` contract.  What changes is everything between the detector and the returned poses:
+box squarify/filter (C ABI host function), the crop batch (fused ROI kernel on the uint8
+frame - the frame crosses PCIe once instead of 3 MiB of float32 per crop), PoseNet (tcgen05
+backbone), Procrustes and yaw nullification (fused head kernel).
+
+Out of scope and therefore injected: the detector/segmenter
+(ultralytics YOLO-seg, GroundingDINO + SAM - third-party models whose weights are not
+available offline) and the depth/translation branch (``get_depth_value`` / ``get_points3d``).
+``detector(rgb) -> (boxes (N,4) int, mask (H,W) uint8)`` and ``depth_fn(good_boxes, depth, mask)
+-> (xyz (N,3), reliable (N,) bool)`` are constructor keywords; without ``depth_fn`` every box is
+kept and translations are zero.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .mvg import filter_very_large_bb
+from .posenet import PoseResNet
+
+
+def _load_intrinsics(intrin_path):
+    """sunflower/utils/io.py:92-98."""
+    if intrin_path is None:
+        return None, None, None
+    import yaml
+    with open(intrin_path, "r") as f:
+        d = yaml.safe_load(f)
+    K = np.array([[d['fx'], 0, d['cx']], [0, d['fy'], d['cy']], [0, 0, 1]])
+    return K, d['h'], d['w']
+
+
+class _PredictorBase:
+    CROP = 512                      # the reference's crop side (pose_predictor.py:145)
+    INTERP = _lib.INTERP_LANCZOS4   # cv2.INTER_LANCZOS4 (pose_predictor.py:145-146)
+    DEPTH_SCALE = 1000.0
+
+    def _init_common(self, device, posenet_path, intrin_path, debug, detector, depth_fn, posenet, max_batch,
+                     crop_hw, interp):
+        self.device = torch.device(device if device != 'cuda' else 'cuda:0')
+        self.debug = debug
+        self.detector = detector
+        self.depth_fn = depth_fn
+        self.crop_hw = crop_hw or self.CROP
+        self.interp = self.INTERP if interp is None else interp
+        if posenet is not None:
+            self.posenet = posenet
+        else:
+            self.posenet = PoseResNet(device=str(self.device), max_batch=max_batch, crop_hw=self.crop_hw)
+            if posenet_path is not None:
+                self.posenet.load_state_dict(torch.load(posenet_path, weights_only=True, map_location="cpu"))
+        self.K, self.height, self.width = _load_intrinsics(intrin_path)
+
+    def _filter_boxes(self, boxes):
+        return boxes
+
+    def get_flower_poses(self, rgb, depth):
+        if self.detector is None:
+            raise _lib.FlopeError("no detector injected: pass detector=callable(rgb)->(boxes, mask)")
+        boxes, mask = self.detector(rgb)
+        boxes = np.asarray(boxes)
+        if boxes.shape[0] == 0:
+            return None
+        boxes = self._filter_boxes(boxes)
+        H, W = rgb.shape[0], rgb.shape[1]
+        # squarify_bb + bb_in_frame over all boxes (fast_pose_predictor.py:69-82)
+        boxes_i32 = np.ascontiguousarray(boxes.reshape(-1, 4), dtype=np.int32)
+        sq_bb, keep = _lib.squarify_filter(boxes_i32, H, W)
+        good_bb = boxes_i32[keep].astype(np.int16)
+        if good_bb.shape[0] == 0:
+            return None
+        xyz = None
+        if self.depth_fn is not None:
+            xyz, reliable = self.depth_fn(good_bb, depth.astype(np.float32) / self.DEPTH_SCALE, mask)
+            sq_bb = sq_bb[reliable]
+            xyz = np.asarray(xyz)[reliable] if len(xyz) == len(reliable) else np.asarray(xyz)
+            if sq_bb.shape[0] == 0:
+                return None
+        rot = self.poses_from_boxes(rgb, mask, sq_bb)
+        Rt = np.repeat(np.eye(4)[None], rot.shape[0], axis=0)      # fast_pose_predictor.py:142-144
+        Rt[:, :3, :3] = rot
+        if xyz is not None:
+            Rt[:, :3, 3] = xyz
+        return Rt
+
+    def poses_from_boxes(self, rgb, mask, sq_bb, nullify_yaw=True):
+        """uint8 frame (H,W,3) + mask (H,W) or None + square in-frame boxes (N,4) -> rotations (N,3,3).
+
+        float64 yaw-nullified (the predictor's output) or float32 raw Procrustes rotations
+        (what scripts/test_posenet.py:144-161 writes) when nullify_yaw=False.
+        """
+        eng = self.posenet.engine
+        with torch.cuda.device(self.device):
+            frame = torch.from_numpy(np.ascontiguousarray(rgb)).to(self.device, non_blocking=True)[None]
+            msk = None if mask is None else torch.from_numpy(np.ascontiguousarray(mask)).to(self.device)[None]
+            b5 = np.zeros((sq_bb.shape[0], 5), np.int32)
+            b5[:, 1:] = sq_bb
+            b5 = torch.from_numpy(b5).to(self.device)
+            _, R, Ry = eng.infer_frames(frame, msk, b5, self.interp, want_R=not nullify_yaw, want_yaw=nullify_yaw)
+            return (Ry if nullify_yaw else R).cpu().numpy()
+
+
+class FastPosePredictor(_PredictorBase):
+    """sunflower/predictor/fast_pose_predictor.py:19-156 (YOLO-seg front end, depth in mm)."""
+    DEPTH_SCALE = 1000.0            # fast_pose_predictor.py:90
+
+    def __init__(self, device: str, yolo_path: str = None, posenet_path: str = None, intrin_path: str = None,
+                 debug: bool = False, *, detector=None, depth_fn=None, posenet=None, max_batch=64, crop_hw=None,
+                 interp=None):
+        self.yolo_path = yolo_path
+        self._init_common(device, posenet_path, intrin_path, debug, detector, depth_fn, posenet, max_batch, crop_hw,
+                          interp)
+
+
+class PosePredictor(_PredictorBase):
+    """sunflower/predictor/pose_predictor.py:40-186 (GroundingDINO + SAM front end, depth in 0.1 mm)."""
+    DEPTH_SCALE = 10000.0           # pose_predictor.py:118
+
+    def __init__(self, device: str, posenet_path: str = None, intrin_path: str = None, debug: bool = False, *,
+                 detector=None, depth_fn=None, posenet=None, max_batch=64, crop_hw=None, interp=None):
+        self._init_common(device, posenet_path, intrin_path, debug, detector, depth_fn, posenet, max_batch, crop_hw,
+                          interp)
+
+    def _filter_boxes(self, boxes):
+        return filter_very_large_bb(boxes)      # pose_predictor.py:83
+
+
+def write_detection_txt(path, det_boxes, rot):
+    """scripts/test_posenet.py:150-161 - one row per flower: xmin ymin xmax ymax u v r00..r22, '%.7f'."""
+    rows = []
+    for bb, R in zip(np.asarray(det_boxes), np.asarray(rot)):
+        xmin, ymin, xmax, ymax = bb
+        rows.append(list(map(float, bb)) + [float((xmin + xmax) / 2), float((ymin + ymax) / 2)] + R.flatten().tolist())
+    np.savetxt(path, np.array(rows), fmt='%.7f')

@@ -1,0 +1,116 @@
+/* flope_b200 - C ABI of the B200-native FloPE pose path.
+ *
+ * The reference (wvu-irl/flope) is pure Python and has no FFI layer; its boundary for this
+ * path is the Python predictor API.  These entry points are what a binding for that API
+ * calls (flope_b200/_lib.py is the ctypes binding; INTEGRATION.md shows the reference-side
+ * stub).  Each declaration cites the reference interface it replaces, as file:line under
+ * the reference root.
+ *
+ * Conventions: return 0 on success or a negative FLOPE_E* code, never throw or exit;
+ * flope_last_error() gives the thread-local message.  Every pointer whose name starts with
+ * d_ is a device pointer on the engine's device; everything else is host memory.  All work
+ * is stream-ordered on the stream argument (a cudaStream_t passed as void*); there is no
+ * hidden device synchronisation: the caller synchronises.  The caller owns every input and
+ * output buffer; the engine owns weights and workspace sized by max_batch.  One engine per
+ * (device, stream): calls on different engines may run concurrently, calls on one engine
+ * may not.
+ */
+#ifndef FLOPE_B200_H
+#define FLOPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLOPE_OK 0
+#define FLOPE_EINVAL (-1)   /* bad argument                       */
+#define FLOPE_ECUDA (-2)    /* CUDA runtime error                 */
+#define FLOPE_ESTATE (-3)   /* weights not loaded / wrong engine  */
+#define FLOPE_ENOMEM (-4)   /* allocation failed                  */
+
+#define FLOPE_INTERP_LINEAR 0     /* cv2.INTER_LINEAR, bit-exact uint8 arithmetic (benchmark mode)  */
+#define FLOPE_INTERP_LANCZOS4 1   /* cv2.INTER_LANCZOS4, bit-exact (the reference's mode)            */
+#define FLOPE_OUT_F32_NCHW 0      /* (B,3,S,S) float32, the tensor the reference builds              */
+#define FLOPE_OUT_ENGINE 1        /* write straight into the engine's bf16 stem input                */
+
+typedef struct flope_engine flope_engine;
+
+/* One entry of PoseResNet.state_dict() (sunflower/models/posenet.py:5-34; key schema in
+ * SURVEY.md appendix E), float32 host data.  num_batches_tracked entries may be omitted. */
+typedef struct flope_tensor_desc {
+  const char* name;
+  const float* data;
+  int ndim;
+  int64_t shape[4];
+} flope_tensor_desc;
+
+int flope_version(void);
+const char* flope_last_error(void);
+
+/* Replaces `PoseResNet().to(device)` (sunflower/predictor/fast_pose_predictor.py:31,
+ * pose_predictor.py:51).  crop_hw is the side of the square crops the engine is sized for
+ * (512 = reference, 224 = benchmark configuration); it must be a multiple of 32. */
+int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_hw);
+void flope_engine_destroy(flope_engine* e);
+
+/* Replaces `posenet.load_state_dict(torch.load(path))` (fast_pose_predictor.py:32,
+ * pose_predictor.py:52).  Folds eval-mode BatchNorm into fp32 scale/bias, packs conv/fc
+ * weights to bf16 tiles, uploads.  Synchronous. */
+int flope_engine_load_weights(flope_engine* e, const flope_tensor_desc* tensors, int n);
+
+/* Replaces squarify_bb + bb_in_frame (sunflower/utils/mvg.py:324-351) as looped at
+ * fast_pose_predictor.py:69-82.  Host function, integer, bit-exact.  boxes_xyxy: (n,4)
+ * int32.  out_sq: (n,4) int32 squarified boxes (all n rows are written); keep[i] = 1 when the
+ * squarified box lies inside the H x W frame. */
+int flope_squarify_filter(const int32_t* boxes_xyxy, int n, int H, int W, int32_t* out_sq, uint8_t* keep);
+
+/* Replaces the crop-batch loop (pose_predictor.py:138-153, fast_pose_predictor.py:108-123,
+ * scripts/test_posenet.py:124-140): slice, cv2.resize of image and mask to (S,S), background
+ * removal, /255, float32, NHWC->NCHW.
+ * d_frames: (n_frames,H,W,3) uint8, frame_stride bytes apart; d_masks: (n_frames,H,W) uint8 or
+ * NULL (== all 255); d_boxes: (n,5) int32 rows [frame, xmin, ymin, xmax, ymax], already squarified
+ * and in-frame.  out_fmt FLOPE_OUT_F32_NCHW writes d_out (n,3,S,S) float32; FLOPE_OUT_ENGINE
+ * ignores d_out and fills the engine's stem input (n <= max_batch, S == crop_hw). */
+int flope_roi_crop(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W, int64_t frame_stride,
+                   const uint8_t* d_masks, const int32_t* d_boxes, int n, int S, int interp, void* d_out,
+                   int out_fmt, void* stream);
+
+/* Replaces `self.posenet(image_batch)` in eval mode (posenet.py:31-34; call sites
+ * fast_pose_predictor.py:126, pose_predictor.py:156, scripts/test_posenet.py:142).
+ * d_in: (n,3,S,S) float32 in [0,1] NCHW, or NULL to run on the stem input already filled by
+ * flope_roi_crop(..., FLOPE_OUT_ENGINE) (then n <= max_batch).  d_r9: (n,9) float32. */
+int flope_posenet_forward(flope_engine* e, const float* d_in, int n, float* d_r9, void* stream);
+
+/* Replaces procrustes_to_rotmat (sunflower/utils/conversion.py:54-58 -> roma.special_procrustes)
+ * and, when d_R_yaw != NULL, nullify_yaw_batch (sunflower/utils/mvg.py:240-251).
+ * d_r9: (n,9) f32.  d_R: (n,9) f32 row-major rotations (nullable).  d_R_yaw: (n,9) f64 (nullable). */
+int flope_pose_head(flope_engine* e, const float* d_r9, int n, float* d_R, double* d_R_yaw, void* stream);
+
+/* nullify_yaw_batch alone (mvg.py:240-251): d_R_in (n,9) f32 rotations -> d_R_yaw (n,9) f64. */
+int flope_nullify_yaw(flope_engine* e, const float* d_R_in, int n, double* d_R_yaw, void* stream);
+
+/* The fused path of get_flower_poses after detection (fast_pose_predictor.py:108-131):
+ * ROI crop -> PoseNet -> Procrustes -> yaw nullification, any n (chunked by max_batch).
+ * Outputs are nullable. */
+int flope_infer_frames(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W, int64_t frame_stride,
+                       const uint8_t* d_masks, const int32_t* d_boxes, int n, int interp, float* d_r9, float* d_R,
+                       double* d_R_yaw, void* stream);
+
+/* Number of kernels the last call on this engine launched (bench.py reports it). */
+int flope_engine_last_launches(const flope_engine* e);
+
+/* ---- test / bring-up hooks (used only by tests/) ---- */
+/* Copy a named intermediate activation of the last forward as (n,C,H,W) float32 into d_out.
+ * Names: "stem", "maxpool", "layer1.0" ... "layer4.1".  Returns C*H*W, or a negative error. */
+int64_t flope_debug_activation(flope_engine* e, const char* name, int n, float* d_out, void* stream);
+/* Evaluate the device mask/normalise arithmetic for all (mask,img) uint8 pairs: d_out (256,256) f32. */
+int flope_debug_normalise_lut(float* d_out, void* stream);
+/* Set a named bring-up option ("swap_lbo_sbo" = 0/1). */
+int flope_debug_set(flope_engine* e, const char* key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOPE_B200_H */
