@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py - PoseNet crops/s of the flope_b200 pose path on B200 (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores
+
+Workload (BASELINE.json configs[1]): PoseNet, batch 256 synthetic 224x224 crops per GPU, random-init
+weights (seed 0), bf16 tensor-core compute with fp32 accumulation.  One step = 256 crops through
+PoseResNet.forward -> Procrustes -> yaw nullification (sunflower/models/posenet.py:31-34,
+sunflower/utils/conversion.py:54-58, sunflower/utils/mvg.py:240-251).
+  value : crops/s with the float32 crop batch already resident in HBM (two alternating 154 MB
+          batches, so inputs alone exceed the 126 MB L2 between consecutive steps)
+  e2e   : the same step through the drop-in module call with HOST buffers: pinned float32 crops ->
+          H2D -> PoseResNet -> pose head -> D2H of the (256,3,3) float64 rotations, every step
+  roofline : the tcgen05 conv/fc kernel family (every backbone layer), timed per launch with CUDA
+          events on the launch stream in a separate instrumented pass of the same step
+  cpu_baseline : the CPU oracle (a restatement of the reference path on torch-CPU fp32) on a bounded
+          sample, rank 0 at N=1 only
+Multi-GPU: weak scaling, crops sharded by batch across ranks, no data-path collective, one final
+NCCL all_gather of the rotations (36 B/crop) inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_CROP = {224: 3.6293e9, 512: 18.952e9}     # 2*MACs, SURVEY.md appendix A
+METRIC = "posenet_crops_per_sec"
+UNIT = "crops/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained"), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")      # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while a region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid):
+        self.uuid = uuid
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.uuid, f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if t < t0 or t > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the CPU oracle, the only place bench.py touches oracle/
+# ---------------------------------------------------------------------------------------------
+def cpu_path_setup(size):
+    import torch
+    from flope_b200 import synth
+    from oracle import posenet as onet
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    net = onet.build(synth.WEIGHT_SEED)
+    return net, cores
+
+
+def cpu_path_step(net, x):
+    """One pass of the reference path on CPU: PoseNet fp32 eval -> Procrustes -> yaw nullification."""
+    from oracle import posenet as onet
+    from oracle import rotation as orot
+    r9 = onet.forward_fp32(net, x, chunk=32)
+    rot = orot.procrustes_to_rotmat(r9).numpy()
+    return orot.nullify_yaw_batch(rot)
+
+
+def cpu_baseline(size, batch, budget_s=12.0):
+    import torch
+    from flope_b200 import synth
+    net, cores = cpu_path_setup(size)
+    n = min(batch, 32)
+    x = synth.mixed_crops(n, size)
+    cpu_path_step(net, x[:4])                                  # warm-up
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        cpu_path_step(net, x)
+        done += n
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{done} crops ({n}-crop batches, {size}x{size}, fp32 torch-CPU eval PoseResNet + Procrustes + "
+                      f"yaw nullification) in {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from flope_b200 import synth
+    net, cores = cpu_path_setup(args.size)
+    probe = synth.mixed_crops(8, args.size)
+    cpu_path_step(net, probe[:2])
+    t0 = time.perf_counter()
+    cpu_path_step(net, probe)
+    per_crop = (time.perf_counter() - t0) / 8
+    total_steps = args.steps + args.warmup
+    n = int(max(1, min(args.batch, 150.0 / total_steps / per_crop)))       # whole run <= ~2.5 min
+    x = synth.mixed_crops(n, args.size)
+    for _ in range(args.warmup):
+        cpu_path_step(net, x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_path_step(net, x)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{n} of the workload's {args.batch} crops per step, {args.steps} steps, {cores} host threads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args):
+    return {"workload": f"PoseNet bf16 batch {args.batch} synthetic {args.size}x{args.size} crops per GPU "
+                        f"(BASELINE.json configs[1]); step = PoseResNet.forward + Procrustes + yaw nullification",
+            "batch_per_gpu": args.batch, "crop_hw": args.size, "weights": "random-init seed 0",
+            "l2_policy": "two alternating float32 input batches of %.0f MB each (> 126 MB L2), activations %.0f MB"
+                         % (args.batch * 3 * args.size * args.size * 4 / 1e6,
+                            args.batch * 4.7 * (args.size / 224.0) ** 2),
+            "parallelism": f"dp{args.gpus} (crops sharded by batch, weights replicated, one final all_gather)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from flope_b200 import _lib, synth
+    from flope_b200.posenet import PoseResNet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, S, K, W = args.batch, args.size, args.steps, args.warmup
+    peaks = load_peaks()
+
+    model = PoseResNet(device=str(dev), max_batch=B, crop_hw=S)
+    model.load_state_dict(synth.random_state_dict(synth.WEIGHT_SEED))
+    eng = model.engine
+
+    xs = [synth.mixed_crops(B, S, seed=synth.CROP_SEED + 10 * rank + i).to(dev) for i in range(2)]
+    r9 = torch.empty((B, 9), dtype=torch.float32, device=dev)
+    results = torch.empty((K, B, 9), dtype=torch.float64, device=dev)               # yaw-nullified rotations
+
+    def step(i, out_slot):
+        eng.posenet_forward(xs[i & 1], out=r9)
+        _lib.check(_lib.lib().flope_pose_head(eng._h, _lib._ptr(r9), B, None, _lib._ptr(results[out_slot]),
+                                              _lib._stream()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i, 0)
+    launches_per_step = 0
+    eng.posenet_forward(xs[0], out=r9)
+    launches_per_step += eng.last_launches() + 1                                       # + the pose-head launch
+    gathered = torch.empty((world, K, B, 9), dtype=torch.float64, device=dev) if world > 1 else None
+
+    uuid = str(torch.cuda.get_device_properties(local).uuid)
+    uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+    sampler = ClockSampler(uuid)
+    sampler.start()
+    time.sleep(0.15)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start = time.time()
+    e0.record()
+    for i in range(K):
+        step(i, i)
+    if world > 1:
+        dist.all_gather_into_tensor(gathered, results)          # the one collective: final gather, 72 B/crop
+    e1.record()
+    barrier()
+    t_end = time.time()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.summary(t_start, t_end)
+    if clocks is None or clocks["samples"] < 3:
+        # region too short for nvidia-smi's sampling period: repeat the same steps untimed for ~1.5 s
+        t_a = time.time()
+        while time.time() - t_a < 1.5:
+            for i in range(20):
+                step(i, 0)
+            torch.cuda.synchronize()
+        clocks = sampler.summary(t_a, time.time()) or {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        clocks["note"] = "timed region shorter than the sampling period; sampled during an untimed repeat of the same steps"
+    sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * K / (ms / 1e3)
+
+    # ---- end to end: host float32 crops -> H2D -> module -> head -> D2H, double buffered ----
+    h_in = [synth.mixed_crops(B, S, seed=synth.CROP_SEED + 10 * rank + i).pin_memory() for i in range(2)]
+    d_in = [torch.empty_like(xs[0]) for _ in range(2)]
+    h_out = [torch.empty((B, 3, 3), dtype=torch.float64).pin_memory() for _ in range(2)]
+    d_out = [torch.empty((B, 3, 3), dtype=torch.float64, device=dev) for _ in range(2)]
+    copy_s, comp_s = torch.cuda.Stream(), torch.cuda.Stream()
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_run(steps):
+        for i in range(steps):
+            b = i & 1
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(ev_done[b])                       # the buffer's previous consumer has finished
+                d_in[b].copy_(h_in[b], non_blocking=True)
+                ev_copied[b].record(copy_s)
+            with torch.cuda.stream(comp_s):
+                comp_s.wait_event(ev_copied[b])
+                out9 = model(d_in[b])                                # the drop-in module call
+                _lib.check(_lib.lib().flope_pose_head(eng._h, _lib._ptr(out9), B, None, _lib._ptr(d_out[b]), _lib._stream()))
+                h_out[b].copy_(d_out[b], non_blocking=True)
+                ev_done[b].record(comp_s)
+        copy_s.synchronize(); comp_s.synchronize()
+
+    e2e_run(max(W, 3))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(K)
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / float(t_e2e.item())
+    h2d = B * 3 * S * S * 4
+    d2h = B * 9 * 8
+
+    # ---- roofline of the dominant kernel family: per-launch CUDA events on the launch stream ----
+    eng.profile(True)
+    prof_steps = 5
+    for i in range(prof_steps):
+        eng.posenet_forward(xs[i & 1], out=r9)
+    prof = eng.profile_read()
+    eng.profile(False)
+    by = {}
+    for name, t in prof:
+        by[name] = by.get(name, 0.0) + t / prof_steps
+    conv_ms = sum(t for n_, t in by.items() if n_.startswith("conv:"))
+    all_ms = sum(by.values())
+    conv_launches = sum(1 for n_ in by if n_.startswith("conv:"))
+    flop = FLOP_PER_CROP.get(S, 3.6293e9 * (S / 224.0) ** 2) * B
+    achieved = flop / (conv_ms / 1e3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"conv_bytes_per_step_b{B}_s{S}")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel<N_TILE,MT> (all %d backbone+fc launches of one step)" % conv_launches,
+                "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
+                "frac_of_sustained_peak": achieved / peaks["tf_sust"] if peaks["tf_sust"] else None,
+                "peak_source": peaks["src"] + " (MEASURED_PEAKS.json burst bf16)" if peaks["src"] == "measured" else "fallback 1.59 PFLOP/s",
+                "traffic": traffic, "algorithmic_flop_per_step": flop, "conv_ms_per_step": conv_ms,
+                "all_kernels_ms_per_step": all_ms, "conv_share_of_step": conv_ms / all_ms if all_ms else None,
+                "per_kernel_ms": {k: round(v, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1])[:8]},
+                "whole_step_frac": (flop / (ms / K / 1e3) / 1e12) / peaks["tf_burst"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "flope_b200.posenet.PoseResNet.__call__ + flope_pose_head on pinned host float32 crops"},
+            "gpu_launches": launches_per_step * K, "roofline": roofline}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(S, B)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

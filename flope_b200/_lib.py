@@ -20,6 +20,7 @@ SYMBOLS = [
     "flope_engine_load_weights", "flope_squarify_filter", "flope_roi_crop", "flope_posenet_forward",
     "flope_pose_head", "flope_nullify_yaw", "flope_infer_frames", "flope_engine_last_launches",
     "flope_debug_activation", "flope_debug_normalise_lut", "flope_debug_set",
+    "flope_engine_profile", "flope_engine_profile_read",
 ]
 
 
@@ -59,6 +60,8 @@ def lib():
         L.flope_debug_activation.restype = C.c_int64
         L.flope_debug_normalise_lut.argtypes = [C.c_void_p, C.c_void_p]
         L.flope_debug_set.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.flope_engine_profile.argtypes = [C.c_void_p, C.c_int]
+        L.flope_engine_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.c_int]
         _lib = L
     return _lib
 
@@ -182,6 +185,16 @@ class Engine:
 
     def last_launches(self):
         return int(lib().flope_engine_last_launches(self._h))
+
+    def profile(self, enable=True):
+        check(lib().flope_engine_profile(self._h, int(enable)))
+
+    def profile_read(self, max_entries=65536):
+        """-> list of (kernel name, milliseconds) for every launch since profile(True)."""
+        names = C.create_string_buffer(max_entries * 24)
+        ms = (C.c_float * max_entries)()
+        n = check(lib().flope_engine_profile_read(self._h, names, len(names), ms, max_entries))
+        return list(zip(names.value.decode().split("\n")[:n], list(ms[:n])))
 
     # -- test hooks ---------------------------------------------------------------
     def debug_activation(self, name, n):

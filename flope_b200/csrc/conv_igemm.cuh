@@ -55,7 +55,6 @@ struct ConvParams {
   int res_base, res_Hp, res_Wp;
   // ---- smem ring sizes ----
   int n_a_slots, n_b_slots;
-  int dbg_swap_lbo_sbo;                // bring-up switch: swap the roles of LBO/SBO in the descriptors
 };
 
 template <int N_TILE, int MT>
@@ -149,10 +148,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // descriptor strides: A planes are a_plane_bytes apart (K direction), 8-pixel groups 128 B apart
-      uint32_t a_lbo = a_plane_bytes, a_sbo = 128, b_lbo = N_TILE * 16, b_sbo = 128;
-      if (p.dbg_swap_lbo_sbo) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
-      const uint64_t a_desc0 = umma_desc(0, a_lbo, a_sbo);
-      const uint64_t b_desc0 = umma_desc(0, b_lbo, b_sbo);
+      const uint64_t a_desc0 = umma_desc(0, /*lbo=*/a_plane_bytes, /*sbo=*/128);
+      const uint64_t b_desc0 = umma_desc(0, /*lbo=*/N_TILE * 16, /*sbo=*/128);
       const uint32_t a_ring_addr = smem_u32(a_ring);
       const uint32_t b_ring_addr = smem_u32(b_ring);
       const int kpairs = p.kc8 >> 1;

@@ -110,7 +110,6 @@ bool conv_launch(int n_tile, int mt, const ConvParams& p, dim3 grid, size_t smem
 struct flope_engine {
   int device = 0, max_batch = 0, S = 0;
   bool weights_loaded = false;
-  int dbg_swap = 0;
   int launches = 0;
   std::vector<ActBuf> bufs;
   std::map<std::string, int> act_names;          // debug name -> buffer index
@@ -121,6 +120,10 @@ struct flope_engine {
   float* d_brot = nullptr;                       // (9,)
   float* d_r9 = nullptr;                         // (max_batch, 9) scratch
   int feat_dim = 2048;
+  // optional per-launch CUDA-event timing (bench.py roofline pass)
+  bool profile = false;
+  std::vector<std::string> prof_names;
+  std::vector<cudaEvent_t> prof_ev;              // start/stop pairs, in launch order
 };
 
 namespace {
@@ -383,11 +386,23 @@ void pack_weights_host(const ConvLayer& L, const float* w, std::vector<__nv_bflo
   }
 }
 
+struct ProfScope {                               // records a start/stop event pair around one launch
+  flope_engine* e; cudaStream_t st; bool on;
+  ProfScope(flope_engine* e_, const std::string& name, cudaStream_t st_) : e(e_), st(st_), on(e_->profile) {
+    if (!on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    e->prof_names.push_back(name); e->prof_ev.push_back(a); e->prof_ev.push_back(b);
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(e->prof_ev.back(), st); }
+};
+
 int run_conv(flope_engine* e, ConvLayer& L, int n, cudaStream_t st) {
+  ProfScope ps(e, "conv:" + L.name, st);
   ConvParams p = L.p;
   p.n_positions = (long long)n * p.Hp * p.Wp;
   p.wgt = L.d_w; p.scale = L.d_scale; p.bias = L.d_bias;
-  p.dbg_swap_lbo_sbo = e->dbg_swap;
   const int TM = L.mt * 128;
   dim3 grid((unsigned)((p.n_positions + TM - 1) / TM), (unsigned)(L.cout / L.n_tile));
   if (!conv_launch(L.n_tile, L.mt, p, grid, L.smem, st)) return fail(FLOPE_EINVAL, "no kernel instance for " + L.name);
@@ -409,6 +424,7 @@ int run_backbone(flope_engine* e, int n, cudaStream_t st) {
     const ActBuf& a = e->bufs[e->buf_stem];
     const ActBuf& b = e->bufs[e->buf_mp_out];
     const long long total = (long long)(a.g.C / 8) * n * b.g.H * b.g.W;
+    ProfScope ps(e, "maxpool", st);
     maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(a.d, a.g, b.d, b.g, n);
     ++e->launches;
   }
@@ -418,6 +434,7 @@ int run_backbone(flope_engine* e, int n, cudaStream_t st) {
     const ActBuf& a = e->bufs[e->buf_pool_in];
     const ActBuf& b = e->bufs[e->buf_pool];
     const int total = (a.g.C / 8) * n;
+    ProfScope ps(e, "avgpool", st);
     avgpool_kernel<<<(total + 127) / 128, 128, 0, st>>>(a.d, a.g, b.d, b.g, n);
     ++e->launches;
   }
@@ -429,6 +446,7 @@ int run_backbone(flope_engine* e, int n, cudaStream_t st) {
 int run_head(flope_engine* e, const float* feat, const float* r9_in, const float* R_in, int n, float* r9_out,
              float* R_out, double* Ryaw_out, cudaStream_t st) {
   const int warps_per_block = 4;
+  ProfScope ps(e, "pose_head", st);
   pose_head_kernel<<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
       feat, e->feat_dim, e->d_wrot, e->d_brot, r9_in, n, r9_out, R_out, Ryaw_out, R_in);
   ++e->launches;
@@ -453,6 +471,7 @@ int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W
   const int block = S >= 256 ? 256 : ((S + 31) / 32 * 32);
   dim3 grid((S + block - 1) / block, (S + rp.rows_per_strip - 1) / rp.rows_per_strip, n);
   const bool has_mask = d_masks != nullptr;
+  ProfScope ps(e, "roi_crop", st);
   if (interp == FLOPE_INTERP_LANCZOS4) {
     if (has_mask) roi_crop_kernel<8, true><<<grid, block, 0, st>>>(rp);
     else roi_crop_kernel<8, false><<<grid, block, 0, st>>>(rp);
@@ -631,6 +650,7 @@ int flope_posenet_forward(flope_engine* e, const float* d_in, int n, float* d_r9
     if (d_in) {
       const ActBuf& x0 = e->bufs[e->buf_x0];
       const long long total = (long long)nb * e->S * e->S;
+      ProfScope ps(e, "ingest", st);
       ingest_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, st>>>(d_in + (size_t)done * 3 * e->S * e->S, nb, e->S, x0.d, x0.g);
       ++e->launches;
     }
@@ -683,6 +703,33 @@ int flope_infer_frames(flope_engine* e, const uint8_t* d_frames, int n_frames, i
 
 int flope_engine_last_launches(const flope_engine* e) { return e ? e->launches : 0; }
 
+int flope_engine_profile(flope_engine* e, int enable) {
+  if (!e) return fail(FLOPE_EINVAL, "NULL argument");
+  for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
+  e->prof_ev.clear(); e->prof_names.clear();
+  e->profile = enable != 0;
+  return FLOPE_OK;
+}
+
+int flope_engine_profile_read(flope_engine* e, char* names, int names_len, float* ms, int max_entries) {
+  if (!e || !names || !ms) return fail(FLOPE_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const int n = (int)e->prof_names.size();
+  if (n > max_entries) return fail(FLOPE_EINVAL, "profile buffer too small");
+  std::string joined;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, e->prof_ev[2 * i], e->prof_ev[2 * i + 1]));
+    ms[i] = t;
+    joined += e->prof_names[i];
+    joined += '\n';
+  }
+  if ((int)joined.size() + 1 > names_len) return fail(FLOPE_EINVAL, "names buffer too small");
+  std::memcpy(names, joined.c_str(), joined.size() + 1);
+  return n;
+}
+
 int64_t flope_debug_activation(flope_engine* e, const char* name, int n, float* d_out, void* stream) {
   if (!e || !name || !d_out) return fail(FLOPE_EINVAL, "NULL argument");
   auto it = e->act_names.find(name);
@@ -704,7 +751,7 @@ int flope_debug_normalise_lut(float* d_out, void* stream) {
 
 int flope_debug_set(flope_engine* e, const char* key, int value) {
   if (!e || !key) return fail(FLOPE_EINVAL, "NULL argument");
-  if (!std::strcmp(key, "swap_lbo_sbo")) { e->dbg_swap = value; return FLOPE_OK; }
+  (void)value;
   return fail(FLOPE_EINVAL, std::string("unknown debug key ") + key);
 }
 

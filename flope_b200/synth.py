@@ -74,3 +74,23 @@ def frames_and_boxes(n_frames=64, boxes_per_frame=32, H=1080, W=1920, seed=FRAME
                 masks[f, y0:y0 + h, x0:x0 + w][e] = 255
             k += 1
     return frames, masks, det
+
+
+def random_state_dict(seed=WEIGHT_SEED):
+    """Random-init PoseResNet weights with the reference's key schema (sunflower/models/posenet.py:5-34).
+
+    Builds the same torch modules in the same order as the reference constructor (torchvision
+    ResNet-18 trunk with weights=None, then base.fc = Linear(512,2048)+ReLU, then fc_rot =
+    Linear(2048,9)), so a given seed yields the same tensors as the reference class built under
+    that seed.  Used for init only - nothing here computes a forward pass.
+    """
+    import torch.nn as nn
+    import torchvision.models as tvm
+    torch.manual_seed(seed)
+    base = tvm.resnet18(weights=None)
+    base.avgpool = nn.AdaptiveAvgPool2d(1)
+    base.fc = nn.Sequential(nn.Linear(512, 2048), nn.ReLU())
+    fc_rot = nn.Linear(2048, 9)
+    sd = {"base." + k: v.detach().clone() for k, v in base.state_dict().items()}
+    sd.update({"fc_rot." + k: v.detach().clone() for k, v in fc_rot.state_dict().items()})
+    return sd

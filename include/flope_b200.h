@@ -101,13 +101,20 @@ int flope_infer_frames(flope_engine* e, const uint8_t* d_frames, int n_frames, i
 /* Number of kernels the last call on this engine launched (bench.py reports it). */
 int flope_engine_last_launches(const flope_engine* e);
 
+/* Per-launch CUDA-event timing for bench.py's roofline pass.  flope_engine_profile(e,1) clears and
+ * enables recording (one start/stop event pair around every kernel launch of subsequent calls);
+ * flope_engine_profile_read synchronises the device and returns the number of recorded launches,
+ * their names as a '\n'-joined string and their durations in milliseconds. */
+int flope_engine_profile(flope_engine* e, int enable);
+int flope_engine_profile_read(flope_engine* e, char* names, int names_len, float* ms, int max_entries);
+
 /* ---- test / bring-up hooks (used only by tests/) ---- */
 /* Copy a named intermediate activation of the last forward as (n,C,H,W) float32 into d_out.
  * Names: "stem", "maxpool", "layer1.0" ... "layer4.1".  Returns C*H*W, or a negative error. */
 int64_t flope_debug_activation(flope_engine* e, const char* name, int n, float* d_out, void* stream);
 /* Evaluate the device mask/normalise arithmetic for all (mask,img) uint8 pairs: d_out (256,256) f32. */
 int flope_debug_normalise_lut(float* d_out, void* stream);
-/* Set a named bring-up option ("swap_lbo_sbo" = 0/1). */
+/* Set a named bring-up option (none defined at present; returns FLOPE_EINVAL for unknown keys). */
 int flope_debug_set(flope_engine* e, const char* key, int value);
 
 #ifdef __cplusplus

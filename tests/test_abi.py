@@ -1,0 +1,78 @@
+"""CPU-side checks of the C-ABI library: it builds, loads, exports every declared symbol,
+its host function is bit-exact with the reference goldens, and it fails loudly without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from flope_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    build.build()
+    return _lib.lib()
+
+
+def test_header_symbols_are_exported(L):
+    hdr = open(os.path.join(ROOT, "include", "flope_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(flope_[a-z0-9_]+)\s*\(", hdr))
+    assert names, "no declarations found"
+    assert names == set(_lib.SYMBOLS)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/flope_b200.h but not exported"
+    assert L.flope_version() >= 100
+
+
+def test_squarify_filter_bit_exact_vs_reference_golden(L, golden_dir):
+    g = np.load(os.path.join(golden_dir, "boxes.npz"))
+    H, W = (int(v) for v in g["frame_hw"])
+    sq, keep = _lib.squarify_filter(np.ascontiguousarray(g["boxes"], dtype=np.int32), H, W)
+    assert np.array_equal(keep, g["keep"])
+    assert np.array_equal(sq, g["squarified"][g["keep"]].astype(np.int32))
+    sq0, keep0 = _lib.squarify_filter(np.zeros((0, 4), np.int32), H, W)
+    assert sq0.shape == (0, 4) and keep0.shape == (0,)
+
+
+def test_python_mirror_matches_reference_golden(golden_dir):
+    from flope_b200 import mvg
+    g = np.load(os.path.join(golden_dir, "boxes.npz"))
+    H, W = g["frame_hw"]
+    got = np.array([mvg.squarify_bb(b) for b in g["boxes"]])
+    assert np.array_equal(got, g["squarified"])
+    assert np.array_equal(np.array([mvg.bb_in_frame(s, (H, W, 3)) for s in got]), g["keep"])
+    assert np.array_equal(mvg.filter_very_large_bb(g["vlb_in"]), g["vlb_out"])
+
+
+def test_errors_are_codes_not_crashes(L):
+    import ctypes as C
+    assert L.flope_engine_create(None, 0, 1, 224) == -1
+    assert b"NULL" in L.flope_last_error()
+    h = C.c_void_p()
+    assert L.flope_engine_create(C.byref(h), 0, 0, 224) == -1
+    assert L.flope_engine_create(C.byref(h), 0, 4, 100) == -1       # crop side must be a multiple of 32
+    assert L.flope_squarify_filter(None, 3, 10, 10, None, None) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    with pytest.raises(_lib.FlopeError):
+        _lib.Engine(0, 4, 224)
+    from flope_b200.conversion import procrustes_to_rotmat
+    with pytest.raises(_lib.FlopeError):
+        procrustes_to_rotmat(torch.zeros(2, 9))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "flope_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "/root/reference" not in src, f

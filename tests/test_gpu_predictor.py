@@ -1,0 +1,77 @@
+"""GPU drop-in test: FastPosePredictor / PosePredictor with an injected detector vs the oracle pipeline."""
+import numpy as np
+import pytest
+import torch
+
+from flope_b200 import synth
+from oracle import pipeline as opipe
+from oracle import posenet as onet
+from oracle import resize as ores
+from oracle import rotation as orot
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def net():
+    return onet.build(synth.WEIGHT_SEED)
+
+
+def _scene(seed=2, n_boxes=6):
+    frames, masks, det = synth.frames_and_boxes(1, n_boxes, H=360, W=640, seed=seed, smooth=True)
+    det = det[0].copy()
+    det[0] = [600, 10, 640, 200]       # squarified box leaves the frame -> dropped by bb_in_frame
+    return frames[0], masks[0], det
+
+
+@pytest.mark.parametrize("crop_hw,interp", [(512, ores.LANCZOS4), (224, ores.BILINEAR)])
+def test_fast_pose_predictor_matches_oracle(net, crop_hw, interp):
+    from flope_b200.posenet import PoseResNet
+    from flope_b200.predictor import FastPosePredictor
+    frame, mask, det = _scene()
+    m = PoseResNet(device="cuda:0", max_batch=8, crop_hw=crop_hw)
+    m.load_state_dict(net.state_dict())
+    pred = FastPosePredictor("cuda:0", detector=lambda rgb: (det.astype(np.int16), mask), posenet=m,
+                             crop_hw=crop_hw, interp=interp)
+    Rt = pred.get_flower_poses(frame, np.zeros(frame.shape[:2], np.uint16))
+    want = opipe.run(net, frame, mask, det, size=crop_hw, interp=interp)
+    assert Rt.dtype == np.float64 and Rt.shape == want["Rt"].shape == (5, 4, 4)
+    assert np.array_equal(Rt[:, 3], np.tile([0, 0, 0, 1.0], (5, 1)))
+    g = orot.geodesic_deg(Rt[:, :3, :3], want["Rt"][:, :3, :3])
+    print("predictor geodesic mean %.4f max %.4f" % (g.mean(), g.max()))
+    assert g.mean() <= 0.5
+    # raw (not yaw-nullified) rotations, the scripts/test_posenet.py output
+    raw = pred.poses_from_boxes(frame, mask, want["sq_boxes"].astype(np.int32), nullify_yaw=False)
+    assert raw.dtype == np.float32
+    assert orot.geodesic_deg(raw, want["rot"]).mean() <= 0.5
+
+
+def test_predictor_returns_none_like_reference(net):
+    from flope_b200.posenet import PoseResNet
+    from flope_b200.predictor import FastPosePredictor, PosePredictor
+    frame, mask, det = _scene()
+    m = PoseResNet(device="cuda:0", max_batch=8, crop_hw=224)
+    m.load_state_dict(net.state_dict())
+    none_boxes = FastPosePredictor("cuda:0", detector=lambda rgb: (np.zeros((0, 4), np.int16), mask), posenet=m,
+                                   crop_hw=224)
+    assert none_boxes.get_flower_poses(frame, None) is None
+    all_out = FastPosePredictor("cuda:0", detector=lambda rgb: (np.array([[600, 10, 640, 200]], np.int16), mask),
+                                posenet=m, crop_hw=224)
+    assert all_out.get_flower_poses(frame, None) is None
+    # PosePredictor applies filter_very_large_bb first (pose_predictor.py:83)
+    big = np.concatenate([det[1:], [[0, 0, 350, 350]]]).astype(np.int64)
+    pp = PosePredictor("cuda:0", detector=lambda rgb: (big, mask), posenet=m, crop_hw=224, interp=ores.BILINEAR)
+    Rt = pp.get_flower_poses(frame, np.zeros(frame.shape[:2], np.uint16))
+    assert Rt.shape == (5, 4, 4)
+
+
+def test_detection_txt_format(tmp_path, net):
+    from flope_b200.predictor import write_detection_txt
+    det = np.array([[10, 20, 110, 121], [5, 6, 50, 60]], np.int16)
+    rot = np.stack([np.eye(3, dtype=np.float32)] * 2)
+    p = tmp_path / "det.txt"
+    write_detection_txt(str(p), det, rot)
+    rows = np.loadtxt(str(p))
+    assert rows.shape == (2, 15)
+    assert np.allclose(rows[0, :6], [10, 20, 110, 121, 60, 70.5])
+    assert open(p).read().split()[0] == "10.0000000"

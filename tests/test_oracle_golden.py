@@ -102,3 +102,11 @@ def test_procrustes_properties():
     for k in range(4):
         dR = torch.from_numpy(sciR.from_rotvec(0.05 * np.random.default_rng(k).normal(size=(M.shape[0], 3))).as_matrix()).float()
         assert torch.all(torch.einsum('nij,nij->n', dR @ r[8:], M) <= base + 1e-4)
+
+
+def test_product_random_init_equals_oracle_init():
+    sd = synth.random_state_dict(synth.WEIGHT_SEED)
+    ref = onet.build(synth.WEIGHT_SEED).state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert torch.equal(sd[k], ref[k]), k

@@ -31,8 +31,7 @@ def main():
     eng = _lib.Engine(0, max_batch=max(a.batch, 8), crop_hw=a.size)
     eng.load_state_dict(net.state_dict())
     xd = x.cuda()
-    for swap in ([0, 1] if a.swap < 0 else [a.swap]):
-        eng.debug_set("swap_lbo_sbo", swap)
+    for swap in [0]:
         r9 = eng.posenet_forward(xd)
         torch.cuda.synchronize()
         print(f"--- swap_lbo_sbo={swap}", flush=True)
