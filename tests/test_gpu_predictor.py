@@ -59,10 +59,13 @@ def test_predictor_returns_none_like_reference(net):
                                 posenet=m, crop_hw=224)
     assert all_out.get_flower_poses(frame, None) is None
     # PosePredictor applies filter_very_large_bb first (pose_predictor.py:83)
-    big = np.concatenate([det[1:], [[0, 0, 350, 350]]]).astype(np.int64)
+    small = np.array([[20 + 70 * i, 30 + 40 * i, 70 + 70 * i, 80 + 40 * i] for i in range(5)], np.int64)
+    big = np.concatenate([small, [[0, 0, 350, 350]]])            # 122500 px^2 > 5 x median (2500 px^2) -> dropped
     pp = PosePredictor("cuda:0", detector=lambda rgb: (big, mask), posenet=m, crop_hw=224, interp=ores.BILINEAR)
     Rt = pp.get_flower_poses(frame, np.zeros(frame.shape[:2], np.uint16))
     assert Rt.shape == (5, 4, 4)
+    fp = FastPosePredictor("cuda:0", detector=lambda rgb: (big, mask), posenet=m, crop_hw=224, interp=ores.BILINEAR)
+    assert fp.get_flower_poses(frame, np.zeros(frame.shape[:2], np.uint16)).shape == (6, 4, 4)
 
 
 def test_detection_txt_format(tmp_path, net):
