@@ -4,14 +4,19 @@
 // (sunflower/models/posenet.py:24-34: base.conv1, layer1..4 convs, downsample convs,
 // base.fc) - SURVEY.md section 2c, K2/K3/K5.
 //
-// One CTA computes TM = MT*128 consecutive pixel positions x N_TILE output channels.
-// In the blocked-pixel layout (common.cuh) a filter tap is a constant position shift, so
-// the A operand of tap (dy,dx) is the *same* shared-memory halo tile read through a UMMA
-// descriptor whose start address is moved by shift*16 bytes: im2col costs nothing and
-// the halo tile is fetched once per 64-channel group instead of once per tap.
-//   warp 0   : TMA producer (cp.async.bulk -> mbarrier complete_tx)
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2-5: epilogue (tcgen05.ld -> folded BN scale/bias, residual, ReLU -> bf16/fp32 store)
+// A tile is TM = MT*128 consecutive pixel positions x N_TILE output channels.  In the
+// blocked-pixel layout (common.cuh) a filter tap is a constant position shift, so the A
+// operand of tap (dy,dx) is the *same* shared-memory halo tile read through a UMMA
+// descriptor whose start address is moved by shift*16 bytes: im2col costs nothing and the
+// halo tile is fetched once per 64-channel group instead of once per tap.
+//
+// Persistent, warp-specialised, one CTA per SM, tiles assigned round-robin:
+//   warp 0   : TMA producer (cp.async.bulk -> mbarrier complete_tx), A-halo ring + weight-tile ring
+//   warp 1   : TMEM allocator + tcgen05.mma issuer (one elected lane; the loop itself is warp-uniform)
+//   warps 2-17: epilogue (tcgen05.ld -> +bias (BN scale is folded into the weights), residual, ReLU -> store);
+//              16 warps so that each SM sub-partition has four of them to hide TMEM/LDG/STG latency
+// The accumulator is double-buffered in TMEM (2 x MT*N_TILE columns), so the epilogue of tile i
+// overlaps the loads and MMAs of tile i+1.
 #pragma once
 #include "common.cuh"
 
@@ -19,7 +24,10 @@ namespace flope {
 
 constexpr int kMaxGroups = 32;
 constexpr int kMaxTaps = 16;
-constexpr int kConvThreads = 192;
+constexpr int kEpiWarps = 16;                  // 4 per TMEM lane quarter
+constexpr int kConvThreads = 64 + 32 * kEpiWarps;
+constexpr int kMaxASlots = 8;
+constexpr int kMaxBSlots = 16;
 
 enum OutMode : int { OUT_PLAIN = 0, OUT_PARITY = 1, OUT_F32_ROWS = 2 };
 
@@ -39,11 +47,11 @@ struct ConvParams {
   // ---- B operand (weights, packed [n_tile][tile][kc8][N_TILE][8] bf16) ----
   const __nv_bfloat16* wgt;
   // ---- position space (validity + (n,h,w) decode) ----
-  long long n_positions;       // N*Hp*Wp
+  int n_positions;             // N*Hp*Wp
   int Hp, Wp, H, W;
+  int n_m_tiles, n_n_tiles;
   // ---- epilogue ----
-  const float* scale;          // [Cout] folded BN scale (1 for fc)
-  const float* bias;           // [Cout] folded BN bias / fc bias
+  const float* bias;           // [Cout] folded BN bias / fc bias (the BN scale is folded into the packed weights)
   int relu;
   int out_mode;
   int Cout;
@@ -57,201 +65,235 @@ struct ConvParams {
   int n_a_slots, n_b_slots;
 };
 
-template <int N_TILE, int MT>
-struct ConvSmem {
-  static constexpr int TM = MT * 128;
-  static size_t a_plane_bytes(int halo) { return (size_t)(TM + halo) * 16; }
-  static size_t bytes(int halo, int kc8, int n_a, int n_b) {
-    return 1024 /*barriers + align slack*/ + (size_t)n_a * kc8 * a_plane_bytes(halo) + (size_t)n_b * kc8 * N_TILE * 16 +
-           2 * N_TILE * sizeof(float);
-  }
-};
-
-template <int N_TILE, int MT>
-__global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+template <int N_TILE, int MT, int KP>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   constexpr int TM = MT * 128;
-  constexpr int TMEM_COLS = (N_TILE * MT < 32) ? 32 : N_TILE * MT;
+  constexpr int ACC_COLS = N_TILE * MT;                         // columns of one accumulator stage
+  constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
   constexpr uint32_t IDESC = umma_idesc_bf16(128, N_TILE);
+  constexpr int NCHUNK = N_TILE / 32;
+  constexpr int KC8 = 2 * KP;                                   // planes per K group
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  // carve: [barriers 512 B][tmem ptr][scale][bias][A ring][B ring]
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* a_empty = a_full + 8;
-  uint64_t* b_full = a_empty + 8;
-  uint64_t* b_empty = b_full + 16;
-  uint64_t* acc_full = b_empty + 16;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
-  float* s_scale = reinterpret_cast<float*>(smem_raw + 512);
-  float* s_bias = s_scale + N_TILE;
+  uint64_t* a_empty = a_full + kMaxASlots;
+  uint64_t* b_full = a_empty + kMaxASlots;
+  uint64_t* b_empty = b_full + kMaxBSlots;
+  uint64_t* acc_full = b_empty + kMaxBSlots;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(smem_raw + 512);
   const int halo = p.halo_before + p.halo_after;
   const uint32_t a_plane_bytes = (uint32_t)(TM + halo) * 16u;
-  const uint32_t a_slot_bytes = a_plane_bytes * p.kc8;
-  const uint32_t b_tile_bytes = (uint32_t)p.kc8 * N_TILE * 16u;
-  uint8_t* a_ring = smem_raw + 512 + 2 * N_TILE * sizeof(float);
-  a_ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a_ring) + 127) & ~uintptr_t(127));
+  const uint32_t a_slot_bytes = a_plane_bytes * KC8;
+  constexpr uint32_t b_tile_bytes = (uint32_t)KC8 * N_TILE * 16u;
+  uint8_t* a_ring = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 512 + (size_t)p.Cout * sizeof(float) + 127) & ~uintptr_t(127));
   uint8_t* b_ring = a_ring + (size_t)p.n_a_slots * a_slot_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long tile_start = (long long)blockIdx.x * TM;
-  const int n_tile = blockIdx.y;
+  const int total_tiles = p.n_m_tiles * p.n_n_tiles;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.n_a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.n_b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
     mbar_fence_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_ptr, TMEM_COLS);
     tmem_relinquish();
   }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < N_TILE; i += 128) {
-      s_scale[i] = p.scale[n_tile * N_TILE + i];
-      s_bias[i] = p.bias[n_tile * N_TILE + i];
-    }
-  }
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer: whole warp runs the loop, one lane issues =====================
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t a_ring_addr = smem_u32(a_ring);
+    const uint32_t b_ring_addr = smem_u32(b_ring);
+    int a_slot = 0, b_slot = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_n_tiles;
+      const int tile_start = (tile / p.n_n_tiles) * TM;
       const __nv_bfloat16* wtile = p.wgt + (size_t)n_tile * p.taps_total * (b_tile_bytes / 2);
-      int b_idx = 0;
       for (int g = 0; g < p.n_groups; ++g) {
-        const int a_slot = g % p.n_a_slots;
-        const uint32_t a_phase = (g / p.n_a_slots) & 1;
         mbar_wait(&a_empty[a_slot], a_phase ^ 1);
-        mbar_expect_tx(&a_full[a_slot], a_slot_bytes);
-        uint8_t* a_dst = a_ring + (size_t)a_slot * a_slot_bytes;
-        for (int j = 0; j < p.kc8; ++j) {
-          const __nv_bfloat16* src =
-              p.in + ((long long)(p.group_plane[g] + j) * p.in_plane + p.in_base + tile_start - p.halo_before) * 8;
-          bulk_g2s(a_dst + (size_t)j * a_plane_bytes, src, a_plane_bytes, &a_full[a_slot]);
-        }
-        for (int t = 0; t < p.group_ntaps[g]; ++t, ++b_idx) {
-          const int b_slot = b_idx % p.n_b_slots;
-          const uint32_t b_phase = (b_idx / p.n_b_slots) & 1;
+        mbar_expect_tx_if(leader, &a_full[a_slot], a_slot_bytes);
+        const uint32_t a_dst = a_ring_addr + a_slot * a_slot_bytes;
+        const __nv_bfloat16* src =
+            p.in + ((long long)p.group_plane[g] * p.in_plane + p.in_base + tile_start - p.halo_before) * 8;
+#pragma unroll
+        for (int j = 0; j < KC8; ++j)
+          bulk_g2s_if(leader, a_dst + j * a_plane_bytes, src + (long long)j * p.in_plane * 8, a_plane_bytes, &a_full[a_slot]);
+        if (++a_slot == p.n_a_slots) { a_slot = 0; a_phase ^= 1; }
+        const int ntaps = p.group_ntaps[g];
+        for (int t = 0; t < ntaps; ++t) {
           mbar_wait(&b_empty[b_slot], b_phase ^ 1);
-          mbar_expect_tx(&b_full[b_slot], b_tile_bytes);
-          bulk_g2s(b_ring + (size_t)b_slot * b_tile_bytes, wtile + (size_t)b_idx * (b_tile_bytes / 2), b_tile_bytes,
-                   &b_full[b_slot]);
+          mbar_expect_tx_if(leader, &b_full[b_slot], b_tile_bytes);
+          bulk_g2s_if(leader, b_ring_addr + b_slot * b_tile_bytes, wtile, b_tile_bytes, &b_full[b_slot]);
+          wtile += b_tile_bytes / 2;
+          if (++b_slot == p.n_b_slots) { b_slot = 0; b_phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // descriptor strides: A planes are a_plane_bytes apart (K direction), 8-pixel groups 128 B apart
-      const uint64_t a_desc0 = umma_desc(0, /*lbo=*/a_plane_bytes, /*sbo=*/128);
-      const uint64_t b_desc0 = umma_desc(0, /*lbo=*/N_TILE * 16, /*sbo=*/128);
-      const uint32_t a_ring_addr = smem_u32(a_ring);
-      const uint32_t b_ring_addr = smem_u32(b_ring);
-      const int kpairs = p.kc8 >> 1;
-      int b_idx = 0;
-      uint32_t first = 1;
+    // ===================== MMA issuer: whole warp runs the loop, one lane issues =====================
+    // Descriptors (K-major, no swizzle): A planes are a_plane_bytes apart in K, 8-pixel groups 128 B apart;
+    // weight tiles are [k8][N_TILE][8], so K-adjacent core matrices are N_TILE*16 B apart.  Only the
+    // 14-bit start-address field changes between MMAs, so each descriptor costs one integer add.
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
+    const uint32_t a_lo0 = ((a_plane_bytes >> 4) << 16) + (smem_u32(a_ring) >> 4) + (uint32_t)p.halo_before;
+    const uint32_t b_lo0 = (((uint32_t)N_TILE * 16u >> 4) << 16) + (smem_u32(b_ring) >> 4);
+    const uint32_t a_kstep = 2u * (a_plane_bytes >> 4);                      // two planes per K=16 MMA
+    constexpr uint32_t b_kstep = 2u * N_TILE;
+    const uint32_t a_slot_units = a_slot_bytes >> 4;
+    constexpr uint32_t b_tile_units = b_tile_bytes >> 4;
+    int a_slot = 0, b_slot = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t stage = it & 1;
+      mbar_wait(&acc_empty[stage], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + stage * ACC_COLS;
+      uint32_t accumulate = 0;
       for (int g = 0; g < p.n_groups; ++g) {
-        const int a_slot = g % p.n_a_slots;
-        const uint32_t a_phase = (g / p.n_a_slots) & 1;
         mbar_wait(&a_full[a_slot], a_phase);
-        const uint32_t a_base = a_ring_addr + a_slot * a_slot_bytes + (uint32_t)p.halo_before * 16u;
+        const uint32_t a_grp = a_lo0 + a_slot * a_slot_units;
         const int tofs = p.group_tapofs[g];
-        for (int t = 0; t < p.group_ntaps[g]; ++t, ++b_idx) {
-          const int b_slot = b_idx % p.n_b_slots;
-          const uint32_t b_phase = (b_idx / p.n_b_slots) & 1;
+        const int ntaps = p.group_ntaps[g];
+        for (int t = 0; t < ntaps; ++t) {
           mbar_wait(&b_full[b_slot], b_phase);
           tc_fence_after();
-          const uint32_t a_tap = a_base + (uint32_t)(p.tap_shift[tofs + t] * 16);
-          const uint32_t b_base = b_ring_addr + b_slot * b_tile_bytes;
+          const uint32_t a_tap = a_grp + (uint32_t)p.tap_shift[tofs + t];    // shift in pixels == 16-byte units
+          const uint32_t b_tap = b_lo0 + b_slot * b_tile_units;
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            for (int k = 0; k < kpairs; ++k) {
-              const uint32_t a_addr = a_tap + (uint32_t)mt * 2048u + (uint32_t)(2 * k) * a_plane_bytes;
-              const uint32_t b_addr = b_base + (uint32_t)(2 * k) * (N_TILE * 16u);
-              umma_bf16(tmem_base + mt * N_TILE, a_desc0 | (uint64_t)((a_addr >> 4) & 0x3FFF),
-                        b_desc0 | (uint64_t)((b_addr >> 4) & 0x3FFF), IDESC, (first && k == 0) ? 0u : 1u);
-            }
+          for (int k = 0; k < KP; ++k) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              umma_bf16_if(leader, acc + mt * N_TILE, a_tap + k * a_kstep + mt * 128u, desc_hi, b_tap + k * b_kstep, desc_hi,
+                           IDESC, (k == 0) ? accumulate : 1u);
           }
-          first = 0;
-          tc_commit(&b_empty[b_slot]);
+          tc_commit_if(leader, &b_empty[b_slot]);          // frees the weight slot once these MMAs retire
+          if (t == ntaps - 1) {
+            tc_commit_if(leader, &a_empty[a_slot]);
+            if (g == p.n_groups - 1) tc_commit_if(leader, &acc_full[stage]);
+          }
+          accumulate = 1;
+          if (++b_slot == p.n_b_slots) { b_slot = 0; b_phase ^= 1; }
         }
-        tc_commit(&a_empty[a_slot]);
+        if (++a_slot == p.n_a_slots) { a_slot = 0; a_phase ^= 1; }
       }
-      tc_commit(acc_full);
     }
   } else {
-    // ===================== epilogue =====================
+    // ===================== epilogue: kEpiWarps warps, 4 per TMEM lane quarter =====================
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
+    const int sub = (warp - 2) >> 2;       // which share of the (mt, 32-column chunk) list
     const int img = p.Hp * p.Wp;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t stage = it & 1;
+      const int n_tile = tile % p.n_n_tiles;
+      const int tile_start = (tile / p.n_n_tiles) * TM;
+      const int cout_base = n_tile * N_TILE;
+      const uint32_t acc = tmem_base + stage * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+      bool waited = false;
 #pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
-      const long long pos = tile_start + mt * 128 + quarter * 32 + lane;
-      const int n = (int)(pos / img);
-      const int r = (int)(pos - (long long)n * img);
-      const int h = r / p.Wp;
-      const int w = r - h * p.Wp;
-      const bool valid = pos < p.n_positions && h < p.H && w < p.W;
-      long long out_pix = 0, res_pix = 0;
-      int out_plane_ofs = 0;
-      if (p.out_mode == OUT_PLAIN) {
-        out_pix = p.out_base + ((long long)n * p.out_Hp + h) * p.out_Wp + w;
-      } else if (p.out_mode == OUT_PARITY) {
-        out_pix = p.out_base + ((long long)n * p.out_Hp + (h >> 1)) * p.out_Wp + (w >> 1);
-        out_plane_ofs = (((h & 1) << 1) | (w & 1)) * (p.Cout >> 3);
-      } else {
-        out_pix = pos;
-      }
-      if (p.res) res_pix = p.res_base + ((long long)n * p.res_Hp + h) * p.res_Wp + w;
-#pragma unroll 1
-      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * N_TILE + c0), acc);
+      for (int c = sub; c < MT * NCHUNK; c += kEpiWarps / 4) {
+        const int mt = c / NCHUNK;
+        const int c0 = (c - mt * NCHUNK) * 32;
+        const int pos = tile_start + mt * 128 + quarter * 32 + lane;
+        const int n = pos / img;
+        const int r = pos - n * img;
+        const int h = r / p.Wp;
+        const int w = r - h * p.Wp;
+        const bool valid = pos < p.n_positions && h < p.H && w < p.W;
+        const int plane0 = (cout_base + c0) >> 3;
+        uint4 res[4];
+        if (p.res != nullptr && valid) {     // issued before the accumulator wait: latency hidden behind the MMAs
+          const __nv_bfloat16* rp = p.res + ((long long)plane0 * p.res_plane + p.res_base + ((long long)n * p.res_Hp + h) * p.res_Wp + w) * 8;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) res[j8] = __ldg(reinterpret_cast<const uint4*>(rp + (long long)j8 * p.res_plane * 8));
+        }
+        if (!waited) {
+          mbar_wait(&acc_full[stage], (it >> 1) & 1);
+          tc_fence_after();
+          waited = true;
+        }
+        uint32_t v32[32];
+        tmem_ld32(acc + (uint32_t)(mt * N_TILE + c0), v32);
         tmem_ld_wait();
+        if (c + kEpiWarps / 4 >= MT * NCHUNK) {
+          // this warp's last TMEM read of the stage: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[stage]);
+        }
         if (valid) {
-          const int cout0 = n_tile * N_TILE + c0;
+          float v[32];
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            float v[8];
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(s_bias + cout_base + c0 + j);
+            v[j] = __uint_as_float(v32[j]) + b.x; v[j + 1] = __uint_as_float(v32[j + 1]) + b.y;
+            v[j + 2] = __uint_as_float(v32[j + 2]) + b.z; v[j + 3] = __uint_as_float(v32[j + 3]) + b.w;
+          }
+          if (p.res != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = c0 + j8 * 8 + j;
-              v[j] = fmaf(__uint_as_float(acc[j8 * 8 + j]), s_scale[c], s_bias[c]);
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const uint4 rr = res[j8];
+              v[j8 * 8 + 0] += bf16_lo(rr.x); v[j8 * 8 + 1] += bf16_hi(rr.x); v[j8 * 8 + 2] += bf16_lo(rr.y); v[j8 * 8 + 3] += bf16_hi(rr.y);
+              v[j8 * 8 + 4] += bf16_lo(rr.z); v[j8 * 8 + 5] += bf16_hi(rr.z); v[j8 * 8 + 6] += bf16_lo(rr.w); v[j8 * 8 + 7] += bf16_hi(rr.w);
             }
-            const int plane = (cout0 >> 3) + j8;
-            if (p.res) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(p.res + ((long long)plane * p.res_plane + res_pix) * 8);
-              v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
-              v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
-            }
-            if (p.relu) {
+          }
+          if (p.out_mode == OUT_F32_ROWS) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)pos * p.Cout + cout_base + c0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < 32; j += 4) {
+              if (p.relu) dst[j >> 2] = make_float4(fmaxf(v[j], 0.f), fmaxf(v[j + 1], 0.f), fmaxf(v[j + 2], 0.f), fmaxf(v[j + 3], 0.f));
+              else dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
-            if (p.out_mode == OUT_F32_ROWS) {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_pix * p.Cout + cout0 + j8 * 8);
-              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-              dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            long long out_pix;
+            int plane = plane0;
+            if (p.out_mode == OUT_PLAIN) {
+              out_pix = p.out_base + ((long long)n * p.out_Hp + h) * p.out_Wp + w;
             } else {
+              out_pix = p.out_base + ((long long)n * p.out_Hp + (h >> 1)) * p.out_Wp + (w >> 1);
+              plane += (((h & 1) << 1) | (w & 1)) * (p.Cout >> 3);
+            }
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)plane * p.out_plane + out_pix) * 8;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
               uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                   ((long long)(plane + out_plane_ofs) * p.out_plane + out_pix) * 8;
-              *reinterpret_cast<uint4*>(dst) = o;
+              if (p.relu) {
+                o.x = pack_bf16x2_relu(v[j8 * 8 + 0], v[j8 * 8 + 1]); o.y = pack_bf16x2_relu(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+                o.z = pack_bf16x2_relu(v[j8 * 8 + 4], v[j8 * 8 + 5]); o.w = pack_bf16x2_relu(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+              } else {
+                o.x = pack_bf16x2(v[j8 * 8 + 0], v[j8 * 8 + 1]); o.y = pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+                o.z = pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]); o.w = pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+              }
+              *reinterpret_cast<uint4*>(dst + (long long)j8 * p.out_plane * 8) = o;
             }
           }
         }
       }
+      if (!waited) {
+        // a warp with no chunk in this configuration still takes part in the accumulator hand-back
+        mbar_wait(&acc_full[stage], (it >> 1) & 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[stage]);
+      }
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();

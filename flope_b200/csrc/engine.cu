@@ -36,7 +36,6 @@ int fail(int code, const std::string& msg) {
   } while (0)
 
 constexpr int kMaxSmem = 232448;      // 227 KB opt-in dynamic shared memory per CTA
-constexpr int kTwoCtaSmem = 113 * 1024;  // budget that lets two CTAs share one SM
 constexpr int kMaxTM = 1024;
 
 long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
@@ -80,26 +79,27 @@ struct ConvLayer {
   float* d_bias = nullptr;
 };
 
-template <int N_TILE, int MT>
+template <int N_TILE, int MT, int KP>
 cudaError_t conv_set_attr() {
-  return cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  return cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, MT, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
 }
-template <int N_TILE, int MT>
+template <int N_TILE, int MT, int KP>
 void conv_launch_t(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  conv_igemm_kernel<N_TILE, MT><<<grid, kConvThreads, smem, st>>>(p);
+  conv_igemm_kernel<N_TILE, MT, KP><<<grid, kConvThreads, smem, st>>>(p);
 }
 
-#define FOR_EACH_CONV_CFG(X) X(64, 1) X(64, 2) X(64, 4) X(64, 8) X(128, 1) X(128, 2) X(128, 4)
+// (N_TILE, MT, KP): output channels per tile, 128-pixel sub-tiles per tile, K=16 MMAs per weight tile
+#define FOR_EACH_CONV_CFG(X) X(64, 4, 4) X(64, 4, 1) X(128, 2, 4)
 
 cudaError_t conv_set_all_attrs() {
   cudaError_t e;
-#define X(N, M) if ((e = conv_set_attr<N, M>()) != cudaSuccess) return e;
+#define X(N, M, K) if ((e = conv_set_attr<N, M, K>()) != cudaSuccess) return e;
   FOR_EACH_CONV_CFG(X)
 #undef X
   return cudaSuccess;
 }
 bool conv_launch(int n_tile, int mt, const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-#define X(N, M) if (n_tile == N && mt == M) { conv_launch_t<N, M>(p, grid, smem, st); return true; }
+#define X(N, M, K) if (n_tile == N && mt == M && p.kc8 == 2 * K) { conv_launch_t<N, M, K>(p, grid, smem, st); return true; }
   FOR_EACH_CONV_CFG(X)
 #undef X
   return false;
@@ -108,7 +108,7 @@ bool conv_launch(int n_tile, int mt, const ConvParams& p, dim3 grid, size_t smem
 }  // namespace
 
 struct flope_engine {
-  int device = 0, max_batch = 0, S = 0;
+  int device = 0, max_batch = 0, S = 0, num_sms = 148;
   bool weights_loaded = false;
   int launches = 0;
   std::vector<ActBuf> bufs;
@@ -269,23 +269,22 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
     p.res_plane = rb.g.plane; p.res_base = rb.g.base; p.res_Hp = rb.g.Hp; p.res_Wp = rb.g.Wp;
   }
 
-  // ---- tile configuration ----
+  // ---- tile configuration: persistent kernel, one CTA per SM, accumulator double-buffered in TMEM ----
   L.n_tile = L.cout >= 128 ? 128 : 64;
-  L.mt = 256 / L.n_tile;                       // 256 TMEM columns -> two CTAs can share an SM
+  L.mt = 256 / L.n_tile;                       // 2 stages x 256 columns = all 512 TMEM columns
   const int halo = p.halo_before + p.halo_after;
   auto smem_of = [&](int n_a, int n_b) {
-    return (size_t)1024 + (size_t)n_a * p.kc8 * (L.mt * 128 + halo) * 16 + (size_t)n_b * p.kc8 * L.n_tile * 16 +
-           2 * L.n_tile * sizeof(float);
+    return (size_t)1024 + (size_t)L.cout * sizeof(float) + (size_t)n_a * p.kc8 * (L.mt * 128 + halo) * 16 +
+           (size_t)n_b * p.kc8 * L.n_tile * 16;
   };
+  // weight tiles are consumed every MT*kc8/2 MMAs, so several must be in flight to cover L2 latency;
+  // halo tiles are consumed once per group: two or three slots are enough.  Rings run across tiles.
   int best_a = 0, best_b = 0;
-  for (int budget : {kTwoCtaSmem, kMaxSmem}) {
-    for (int n_b : {4, 3, 2}) {
-      const int nb = std::min(n_b, p.taps_total);
-      int n_a = std::min(p.n_groups, 4);
-      while (n_a >= 1 && smem_of(n_a, nb) > (size_t)budget) --n_a;
-      if (n_a >= 1) { best_a = n_a; best_b = nb; break; }
-    }
-    if (best_a) break;
+  for (int n_b : {8, 6, 4, 3, 2}) {
+    if (p.kc8 == 2) n_b = kMaxBSlots;          // stem: 2 KB weight tiles
+    int n_a = p.kc8 == 2 ? 4 : 3;
+    while (n_a >= 1 && smem_of(n_a, n_b) > (size_t)kMaxSmem) --n_a;
+    if (n_a >= 2 || (n_a == 1 && n_b == 2)) { best_a = n_a; best_b = n_b; break; }
   }
   if (!best_a) return fail(FLOPE_EINVAL, "conv layer " + L.name + " does not fit in shared memory");
   p.n_a_slots = best_a; p.n_b_slots = best_b;
@@ -341,7 +340,7 @@ int build_network(flope_engine* e) {
   return FLOPE_OK;
 }
 
-void pack_weights_host(const ConvLayer& L, const float* w, std::vector<__nv_bfloat16>& out) {
+void pack_weights_host(const ConvLayer& L, const float* w, const std::vector<float>& scale, std::vector<__nv_bfloat16>& out) {
   const ConvParams& p = L.p;
   const int NT = L.n_tile;
   const int n_tiles = L.cout / NT;
@@ -379,7 +378,7 @@ void pack_weights_host(const ConvLayer& L, const float* w, std::vector<__nv_bflo
                   break;
                 }
               }
-              dst[((size_t)k8 * NT + n) * 8 + j] = __float2bfloat16_rn(v);
+              dst[((size_t)k8 * NT + n) * 8 + j] = __float2bfloat16_rn(v * scale[co]);   // BN scale folded in before the bf16 rounding
             }
       }
     }
@@ -401,10 +400,12 @@ struct ProfScope {                               // records a start/stop event p
 int run_conv(flope_engine* e, ConvLayer& L, int n, cudaStream_t st) {
   ProfScope ps(e, "conv:" + L.name, st);
   ConvParams p = L.p;
-  p.n_positions = (long long)n * p.Hp * p.Wp;
-  p.wgt = L.d_w; p.scale = L.d_scale; p.bias = L.d_bias;
+  p.n_positions = n * p.Hp * p.Wp;
+  p.wgt = L.d_w; p.bias = L.d_bias;
   const int TM = L.mt * 128;
-  dim3 grid((unsigned)((p.n_positions + TM - 1) / TM), (unsigned)(L.cout / L.n_tile));
+  p.n_m_tiles = (p.n_positions + TM - 1) / TM;
+  p.n_n_tiles = L.cout / L.n_tile;
+  dim3 grid((unsigned)std::min(p.n_m_tiles * p.n_n_tiles, e->num_sms));
   if (!conv_launch(L.n_tile, L.mt, p, grid, L.smem, st)) return fail(FLOPE_EINVAL, "no kernel instance for " + L.name);
   ++e->launches;
   return FLOPE_OK;
@@ -514,6 +515,7 @@ int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_
   CUDA_TRY(conv_set_all_attrs());
   flope_engine* e = new flope_engine();
   e->device = device; e->max_batch = max_batch; e->S = crop_hw;
+  e->num_sms = prop.multiProcessorCount;
   int rc = build_network(e);
   if (rc) { delete e; return rc; }
   for (ActBuf& b : e->bufs) {
@@ -580,7 +582,7 @@ int flope_engine_load_weights(flope_engine* e, const flope_tensor_desc* tensors,
       for (int c = 0; c < L.cout; ++c) bias[c] = b[c];
     }
     std::vector<__nv_bfloat16> packed;
-    pack_weights_host(L, w, packed);
+    pack_weights_host(L, w, scale, packed);
     cudaFree(L.d_w); cudaFree(L.d_scale); cudaFree(L.d_bias);
     L.d_w = nullptr; L.d_scale = nullptr; L.d_bias = nullptr;
     CUDA_TRY(cudaMalloc(&L.d_w, packed.size() * sizeof(__nv_bfloat16)));
