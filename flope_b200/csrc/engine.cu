@@ -120,6 +120,11 @@ struct flope_engine {
   float* d_brot = nullptr;                       // (9,)
   float* d_r9 = nullptr;                         // (max_batch, 9) scratch
   int feat_dim = 2048;
+  // CUDA graphs of the backbone (stem .. fc), one per batch size, captured on an engine-owned stream
+  bool use_graph = true;
+  cudaStream_t cap_stream = nullptr;
+  struct GraphEntry { int n; int launches; cudaGraphExec_t exec; };
+  std::vector<GraphEntry> graphs;
   // optional per-launch CUDA-event timing (bench.py roofline pass)
   bool profile = false;
   std::vector<std::string> prof_names;
@@ -417,7 +422,7 @@ int grid_for(long long total, int block) {
 }
 
 // Backbone + fc on the stem input already present in buf_x0; leaves features in d_feat.
-int run_backbone(flope_engine* e, int n, cudaStream_t st) {
+int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
   int rc;
   size_t li = 0;
   if ((rc = run_conv(e, e->layers[li++], n, st))) return rc;       // stem
@@ -434,21 +439,56 @@ int run_backbone(flope_engine* e, int n, cudaStream_t st) {
   {
     const ActBuf& a = e->bufs[e->buf_pool_in];
     const ActBuf& b = e->bufs[e->buf_pool];
-    const int total = (a.g.C / 8) * n;
+    const int total_warps = (a.g.C / 8) * n;
     ProfScope ps(e, "avgpool", st);
-    avgpool_kernel<<<(total + 127) / 128, 128, 0, st>>>(a.d, a.g, b.d, b.g, n);
+    avgpool_kernel<<<(total_warps + 7) / 8, 256, 0, st>>>(a.d, a.g, b.d, b.g, n);
     ++e->launches;
   }
   if ((rc = run_conv(e, e->layers[li], n, st))) return rc;         // fc
-  CUDA_TRY(cudaGetLastError());
+  if (e->cap_stream == nullptr || st != e->cap_stream) CUDA_TRY(cudaGetLastError());
+  return FLOPE_OK;
+}
+
+void drop_graphs(flope_engine* e) {
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+}
+
+// The ~23 backbone launches of one batch size are captured once into a CUDA graph (engine-internal
+// buffers only, so every kernel argument is fixed for a given n) and replayed with one launch.
+int run_backbone(flope_engine* e, int n, cudaStream_t st) {
+  if (!e->use_graph || e->profile) return run_backbone_launches(e, n, st);
+  for (auto& g : e->graphs)
+    if (g.n == n) {
+      CUDA_TRY(cudaGraphLaunch(g.exec, st));
+      e->launches += g.launches;
+      return FLOPE_OK;
+    }
+  if (!e->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+  const int before = e->launches;
+  CUDA_TRY(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+  int rc = run_backbone_launches(e, n, e->cap_stream);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+  const int launches = e->launches - before;
+  e->launches = before;
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return fail(FLOPE_ECUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return fail(FLOPE_ECUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
+  if (e->graphs.size() >= 16) { cudaGraphExecDestroy(e->graphs.front().exec); e->graphs.erase(e->graphs.begin()); }
+  e->graphs.push_back({n, launches, exec});
+  CUDA_TRY(cudaGraphLaunch(exec, st));
+  e->launches += launches;
   return FLOPE_OK;
 }
 
 int run_head(flope_engine* e, const float* feat, const float* r9_in, const float* R_in, int n, float* r9_out,
              float* R_out, double* Ryaw_out, cudaStream_t st) {
-  const int warps_per_block = 4;
   ProfScope ps(e, "pose_head", st);
-  pose_head_kernel<<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+  pose_head_kernel<<<n, kHeadThreads, 0, st>>>(
       feat, e->feat_dim, e->d_wrot, e->d_brot, r9_in, n, r9_out, R_out, Ryaw_out, R_in);
   ++e->launches;
   CUDA_TRY(cudaGetLastError());
@@ -536,6 +576,8 @@ int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_
 void flope_engine_destroy(flope_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
+  drop_graphs(e);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (ActBuf& b : e->bufs) cudaFree(b.d);
   for (ConvLayer& L : e->layers) { cudaFree(L.d_w); cudaFree(L.d_scale); cudaFree(L.d_bias); }
   cudaFree(e->d_feat); cudaFree(e->d_wrot); cudaFree(e->d_brot); cudaFree(e->d_r9);
@@ -545,6 +587,7 @@ void flope_engine_destroy(flope_engine* e) {
 int flope_engine_load_weights(flope_engine* e, const flope_tensor_desc* tensors, int n) {
   if (!e || !tensors) return fail(FLOPE_EINVAL, "NULL argument");
   CUDA_TRY(cudaSetDevice(e->device));
+  drop_graphs(e);                              // captured kernel arguments point at the old weight buffers
   std::map<std::string, const flope_tensor_desc*> sd;
   for (int i = 0; i < n; ++i)
     if (tensors[i].name && tensors[i].data) sd[tensors[i].name] = &tensors[i];
@@ -651,7 +694,7 @@ int flope_posenet_forward(flope_engine* e, const float* d_in, int n, float* d_r9
     const int nb = std::min(e->max_batch, n - done);
     if (d_in) {
       const ActBuf& x0 = e->bufs[e->buf_x0];
-      const long long total = (long long)nb * e->S * e->S;
+      const long long total = (long long)nb * e->S * (e->S / 4);
       ProfScope ps(e, "ingest", st);
       ingest_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, st>>>(d_in + (size_t)done * 3 * e->S * e->S, nb, e->S, x0.d, x0.g);
       ++e->launches;
@@ -753,7 +796,7 @@ int flope_debug_normalise_lut(float* d_out, void* stream) {
 
 int flope_debug_set(flope_engine* e, const char* key, int value) {
   if (!e || !key) return fail(FLOPE_EINVAL, "NULL argument");
-  (void)value;
+  if (!std::strcmp(key, "use_graph")) { e->use_graph = value != 0; return FLOPE_OK; }
   return fail(FLOPE_EINVAL, std::string("unknown debug key ") + key);
 }
 

@@ -12,21 +12,29 @@ namespace flope {
 // holds 8 bf16: [bx=0: c0 c1 c2 0 | bx=1: c0 c1 c2 0].
 __global__ void ingest_nchw_f32_kernel(const float* __restrict__ x, int n, int S, __nv_bfloat16* __restrict__ out,
                                        Geom g) {
-  const long long total = (long long)n * S * S;
+  // one thread = 4 consecutive pixels of one row: three 16-byte loads (one per channel plane),
+  // one 32-byte run of two s2d pixels out
+  const int S4 = S >> 2;
+  const long long total = (long long)n * S * S4;
+  const long long plane_sz = (long long)S * S;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int xx = (int)(i % S);
-    const int yy = (int)((i / S) % S);
-    const int b = (int)(i / ((long long)S * S));
-    const float* px = x + ((long long)b * 3 * S + yy) * S + xx;
-    const long long plane_sz = (long long)S * S;
-    const float c0 = px[0], c1 = px[plane_sz], c2 = px[2 * plane_sz];
-    uint2 o;
-    o.x = pack_bf16x2(c0, c1);
-    o.y = pack_bf16x2(c2, 0.f);
-    const long long pos = g.base + geom_pos(g, b, yy >> 1, xx >> 1);
-    __nv_bfloat16* dst = out + ((long long)(yy & 1) * g.plane + pos) * 8 + (xx & 1) * 4;
-    *reinterpret_cast<uint2*>(dst) = o;
+    const int x4 = (int)(i % S4);
+    const int yy = (int)((i / S4) % S);
+    const int b = (int)(i / ((long long)S4 * S));
+    const float* px = x + ((long long)b * 3 * S + yy) * S + 4 * x4;
+    const float4 c0 = __ldcs(reinterpret_cast<const float4*>(px));
+    const float4 c1 = __ldcs(reinterpret_cast<const float4*>(px + plane_sz));
+    const float4 c2 = __ldcs(reinterpret_cast<const float4*>(px + 2 * plane_sz));
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(c0.x, c1.x); o0.y = pack_bf16x2(c2.x, 0.f);
+    o0.z = pack_bf16x2(c0.y, c1.y); o0.w = pack_bf16x2(c2.y, 0.f);
+    o1.x = pack_bf16x2(c0.z, c1.z); o1.y = pack_bf16x2(c2.z, 0.f);
+    o1.z = pack_bf16x2(c0.w, c1.w); o1.w = pack_bf16x2(c2.w, 0.f);
+    const long long pos = g.base + geom_pos(g, b, yy >> 1, 2 * x4);
+    uint4* dst = reinterpret_cast<uint4*>(out + ((long long)(yy & 1) * g.plane + pos) * 8);
+    dst[0] = o0;
+    dst[1] = o1;
   }
 }
 
@@ -64,29 +72,38 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, Geom g
   }
 }
 
-// One thread per (c8 plane, crop): mean of H*W pixels in fp32, written as bf16 into the
-// "one pixel per crop" blocked tensor the fc GEMM reads (plane c8, position = crop index).
+// One warp per (c8 plane, crop): lanes stride over the H*W pixels (16-byte loads), fp32 partial sums,
+// xor-shuffle reduction; lane 0 writes the bf16 means into the "one pixel per crop" blocked tensor the
+// fc GEMM reads (plane c8, position = crop index).
 __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ in, Geom gi, __nv_bfloat16* __restrict__ out,
                                Geom go, int n) {
   const int C8 = gi.C >> 3;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C8 * n) return;
-  const int b = i % n;
-  const int c8 = i / n;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= C8 * n) return;
+  const int b = wid % n;
+  const int c8 = wid / n;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const __nv_bfloat16* src = in + ((long long)c8 * gi.plane + gi.base) * 8;
-  for (int h = 0; h < gi.H; ++h) {
-    for (int w = 0; w < gi.W; ++w) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src + geom_pos(gi, b, h, w) * 8);
-      s[0] += bf16_lo(v.x); s[1] += bf16_hi(v.x); s[2] += bf16_lo(v.y); s[3] += bf16_hi(v.y);
-      s[4] += bf16_lo(v.z); s[5] += bf16_hi(v.z); s[6] += bf16_lo(v.w); s[7] += bf16_hi(v.w);
-    }
+  const int hw = gi.H * gi.W;
+  for (int i = lane; i < hw; i += 32) {
+    const int h = i / gi.W, w = i - h * gi.W;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + geom_pos(gi, b, h, w) * 8);
+    s[0] += bf16_lo(v.x); s[1] += bf16_hi(v.x); s[2] += bf16_lo(v.y); s[3] += bf16_hi(v.y);
+    s[4] += bf16_lo(v.z); s[5] += bf16_hi(v.z); s[6] += bf16_lo(v.w); s[7] += bf16_hi(v.w);
   }
-  const float inv = 1.0f / (float)(gi.H * gi.W);
-  uint4 o;
-  o.x = pack_bf16x2(s[0] * inv, s[1] * inv); o.y = pack_bf16x2(s[2] * inv, s[3] * inv);
-  o.z = pack_bf16x2(s[4] * inv, s[5] * inv); o.w = pack_bf16x2(s[6] * inv, s[7] * inv);
-  *reinterpret_cast<uint4*>(out + ((long long)c8 * go.plane + go.base + b) * 8) = o;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+  }
+  if (lane == 0) {
+    const float inv = 1.0f / (float)hw;
+    uint4 o;
+    o.x = pack_bf16x2(s[0] * inv, s[1] * inv); o.y = pack_bf16x2(s[2] * inv, s[3] * inv);
+    o.z = pack_bf16x2(s[4] * inv, s[5] * inv); o.w = pack_bf16x2(s[6] * inv, s[7] * inv);
+    *reinterpret_cast<uint4*>(out + ((long long)c8 * go.plane + go.base + b) * 8) = o;
+  }
 }
 
 // parity = 0: plain tensor.  parity = 1: parity-split tensor whose Geom describes the half-res grid

@@ -5,8 +5,8 @@
 //                       sunflower/utils/conversion.py:54-58 (roma.special_procrustes)
 //   nullify yaw       : Euler 'zyx', zero the z angle, recompose  sunflower/utils/mvg.py:240-251
 //
-// One warp per crop: the 2048-long dot products are a coalesced warp reduction (shuffle tree),
-// then lane 0 does the 3x3 projection in fp64 (9 values per crop; costs nothing and keeps the
+// One CTA per crop: the 2048-long dot products are a coalesced block reduction (shuffle tree + smem),
+// then thread 0 does the 3x3 projection in fp64 (9 values per crop; costs nothing and keeps the
 // near-degenerate random-init heads of SURVEY.md H3 stable).
 #pragma once
 #include "common.cuh"
@@ -105,24 +105,27 @@ __device__ inline void nullify_yaw3(const double R[3][3], double Y[3][3]) {
   Y[2][0] = -cg * sb; Y[2][1] = sg;  Y[2][2] = cg * cb;
 }
 
-// feat: (n, K) fp32 features (post-ReLU) or nullptr when r9_in is given.
+// One CTA (128 threads) per crop.  feat: (n, K) fp32 features (post-ReLU) or nullptr when r9_in / R_in is given.
 // Outputs (each nullable): r9 (n,9) f32, R (n,9) f32 row-major, R_yaw (n,9) f64 row-major.
-__global__ void pose_head_kernel(const float* __restrict__ feat, int K, const float* __restrict__ w_rot,
-                                 const float* __restrict__ b_rot, const float* __restrict__ r9_in, int n,
-                                 float* __restrict__ r9_out, float* __restrict__ R_out, double* __restrict__ Ryaw_out,
-                                 const float* __restrict__ R_in) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= n) return;
-  float r9[9];
+constexpr int kHeadThreads = 128;
+__global__ void __launch_bounds__(kHeadThreads) pose_head_kernel(const float* __restrict__ feat, int K,
+                                                                 const float* __restrict__ w_rot,
+                                                                 const float* __restrict__ b_rot,
+                                                                 const float* __restrict__ r9_in, int n,
+                                                                 float* __restrict__ r9_out, float* __restrict__ R_out,
+                                                                 double* __restrict__ Ryaw_out,
+                                                                 const float* __restrict__ R_in) {
+  __shared__ float s_part[kHeadThreads / 32][9];
+  const int crop = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (feat) {
     float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const float4* f4 = reinterpret_cast<const float4*>(feat + (size_t)warp * K);
-    for (int k = lane; k < (K >> 2); k += 32) {
+    const float4* f4 = reinterpret_cast<const float4*>(feat + (size_t)crop * K);
+    for (int k = threadIdx.x; k < (K >> 2); k += kHeadThreads) {
       const float4 f = f4[k];
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
-        const float4 w = reinterpret_cast<const float4*>(w_rot + (size_t)j * K)[k];
+        const float4 w = __ldg(reinterpret_cast<const float4*>(w_rot + (size_t)j * K) + k);
         acc[j] = fmaf(f.x, w.x, fmaf(f.y, w.y, fmaf(f.z, w.z, fmaf(f.w, w.w, acc[j]))));
       }
     }
@@ -130,31 +133,42 @@ __global__ void pose_head_kernel(const float* __restrict__ feat, int K, const fl
     for (int j = 0; j < 9; ++j) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-      r9[j] = acc[j] + b_rot[j];
+      if (lane == 0) s_part[warp][j] = acc[j];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  float r9[9];
+  if (feat) {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      float t = b_rot[j];
+#pragma unroll
+      for (int w = 0; w < kHeadThreads / 32; ++w) t += s_part[w][j];
+      r9[j] = t;
     }
   } else if (r9_in) {
 #pragma unroll
-    for (int j = 0; j < 9; ++j) r9[j] = r9_in[(size_t)warp * 9 + j];
+    for (int j = 0; j < 9; ++j) r9[j] = r9_in[(size_t)crop * 9 + j];
   }
-  if (lane != 0) return;
   double R[3][3];
   if (R_in) {                                   // yaw-only mode (mvg.nullify_yaw_batch mirror)
-    for (int j = 0; j < 9; ++j) R[j / 3][j % 3] = (double)R_in[(size_t)warp * 9 + j];
+    for (int j = 0; j < 9; ++j) R[j / 3][j % 3] = (double)R_in[(size_t)crop * 9 + j];
   } else {
     double M[3][3];
     for (int j = 0; j < 9; ++j) M[j / 3][j % 3] = (double)r9[j];
     special_procrustes3(M, R);
     if (r9_out)
-      for (int j = 0; j < 9; ++j) r9_out[(size_t)warp * 9 + j] = r9[j];
+      for (int j = 0; j < 9; ++j) r9_out[(size_t)crop * 9 + j] = r9[j];
     if (R_out)
-      for (int j = 0; j < 9; ++j) R_out[(size_t)warp * 9 + j] = (float)R[j / 3][j % 3];
+      for (int j = 0; j < 9; ++j) R_out[(size_t)crop * 9 + j] = (float)R[j / 3][j % 3];
   }
   if (Ryaw_out) {
     // the reference hands the fp32 rotation to SciPy, so yaw nullification starts from the fp32-rounded R
     double Rf[3][3], Y[3][3];
     for (int j = 0; j < 9; ++j) Rf[j / 3][j % 3] = (double)(float)R[j / 3][j % 3];
     nullify_yaw3(Rf, Y);
-    for (int j = 0; j < 9; ++j) Ryaw_out[(size_t)warp * 9 + j] = Y[j / 3][j % 3];
+    for (int j = 0; j < 9; ++j) Ryaw_out[(size_t)crop * 9 + j] = Y[j / 3][j % 3];
   }
 }
 

@@ -114,7 +114,7 @@ int flope_engine_profile_read(flope_engine* e, char* names, int names_len, float
 int64_t flope_debug_activation(flope_engine* e, const char* name, int n, float* d_out, void* stream);
 /* Evaluate the device mask/normalise arithmetic for all (mask,img) uint8 pairs: d_out (256,256) f32. */
 int flope_debug_normalise_lut(float* d_out, void* stream);
-/* Set a named bring-up option (none defined at present; returns FLOPE_EINVAL for unknown keys). */
+/* Set a named option: "use_graph" = 0/1 (replay the backbone as a CUDA graph; default 1). */
 int flope_debug_set(flope_engine* e, const char* key, int value);
 
 #ifdef __cplusplus

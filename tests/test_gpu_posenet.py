@@ -112,3 +112,14 @@ def test_posenet_dropin_class(net):
     assert _rel(out.cpu(), want) < 2e-2
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 100, 100, device="cuda"))
+
+
+def test_graph_replay_equals_direct_launches(eng224):
+    x = synth.mixed_crops(12, 224).cuda()
+    eng224.debug_set("use_graph", 0)
+    a = eng224.posenet_forward(x).clone()
+    eng224.debug_set("use_graph", 1)
+    b = eng224.posenet_forward(x).clone()      # captures
+    c = eng224.posenet_forward(x).clone()      # replays
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, c)
