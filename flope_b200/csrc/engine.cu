@@ -517,8 +517,8 @@ int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W
     if (has_mask) roi_crop_kernel<8, true><<<grid, block, 0, st>>>(rp);
     else roi_crop_kernel<8, false><<<grid, block, 0, st>>>(rp);
   } else {
-    if (has_mask) roi_crop_kernel<2, true><<<grid, block, 0, st>>>(rp);
-    else roi_crop_kernel<2, false><<<grid, block, 0, st>>>(rp);
+    if (has_mask) roi_bilinear_kernel<true><<<grid, block, 0, st>>>(rp);
+    else roi_bilinear_kernel<false><<<grid, block, 0, st>>>(rp);
   }
   ++e->launches;
   CUDA_TRY(cudaGetLastError());
@@ -527,7 +527,7 @@ int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W
 
 __global__ void normalise_lut_kernel(float* out) {
   const int i = threadIdx.x, m = blockIdx.x;
-  out[m * 256 + i] = __fdiv_rn((float)(i * m), 65025.f);
+  out[m * 256 + i] = normalise_u8(i, m);
 }
 
 }  // namespace

@@ -86,6 +86,137 @@ __device__ inline void linear_coefs(int d, double scale, int src, bool vertical,
   s_out = s;
 }
 
+// float32((double(img) * (double(mask)/255.0)) / 255.0) == correctly rounded fp32 (img*mask)/65025 for all
+// 65536 (img,mask) pairs (tests/test_oracle_resize.py).  One reciprocal multiply plus one exact-residual
+// correction step gives that correctly rounded quotient for every integer numerator 0..65025; the device
+// result is checked exhaustively against the oracle table in tests/test_gpu_roi.py.
+__device__ __forceinline__ float normalise_u8(int img, int mask) {
+  const float x = (float)(img * mask);
+  const float r = 1.0f / 65025.0f;
+  const float q = x * r;
+  const float e = fmaf(-q, 65025.0f, x);
+  return fmaf(e, r, q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bilinear (cv2.INTER_LINEAR, uint8-exact) specialisation: the benchmark mode.
+// Thread = one output column marching down a strip.  Two horizontally filtered source rows are kept
+// (pre-shifted by 4 as cv2's vertical pass wants them); the vertical pass is two IMAD.HI per channel:
+//   ((b*(S>>4))>>16) == mulhi(b<<16, S>>4).   The result never leaves [0,255], so no saturation is needed.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(256, 7) roi_bilinear_kernel(const __grid_constant__ RoiParams p) {
+  constexpr int NCH = HAS_MASK ? 4 : 3;
+  __shared__ int s_sy[kRoiMaxStripRows];
+  __shared__ uint32_t s_b0[kRoiMaxStripRows];
+  __shared__ uint32_t s_b1[kRoiMaxStripRows];
+  __shared__ float s_lut[256];             // normalise_u8(i, 255): the value of an unmasked / fully masked-in pixel
+
+  const int crop = blockIdx.z;
+  const int32_t* bx = p.boxes + (size_t)crop * 5;
+  const int frame = bx[0], xmin = bx[1], ymin = bx[2];
+  const int sw = bx[3] - bx[1], sh = bx[4] - bx[2];
+  const int S = p.S;
+  const int y_begin = blockIdx.y * p.rows_per_strip;
+  const int y_end = min(S, y_begin + p.rows_per_strip);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sw <= 0 || sh <= 0) return;
+
+  const double scale_x = 1.0 / ((double)S / (double)sw);
+  const double scale_y = 1.0 / ((double)S / (double)sh);
+  for (int r = threadIdx.x; r < y_end - y_begin; r += blockDim.x) {
+    short ic[2];
+    int sy;
+    linear_coefs(y_begin + r, scale_y, sh, true, sy, ic);
+    s_sy[r] = sy;
+    s_b0[r] = (uint32_t)(int)ic[0] << 16;
+    s_b1[r] = (uint32_t)(int)ic[1] << 16;
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = normalise_u8(i, 255);
+  __syncthreads();
+  if (x >= S) return;
+
+  int cx0, cx1;
+  uint32_t oa, ob, ma, mb;                 // 32-bit byte offsets of the two horizontal taps inside the crop
+  {
+    short ic[2];
+    int sx;
+    linear_coefs(x, scale_x, sw, false, sx, ic);
+    const int x0 = min(max(sx, 0), sw - 1);
+    const int x1 = min(max(sx + 1, 0), sw - 1);
+    cx0 = ic[0]; cx1 = ic[1];
+    oa = x0 * 3; ob = x1 * 3; ma = x0; mb = x1;
+  }
+  const uint8_t* img = p.frames + (long long)frame * p.frame_stride + ((long long)ymin * p.W + xmin) * 3;
+  const uint8_t* msk = HAS_MASK ? p.masks + (long long)frame * p.mask_stride + (long long)ymin * p.W + xmin : nullptr;
+  const uint32_t row_bytes = (uint32_t)p.W * 3u;
+
+  uint32_t h0[NCH], h1[NCH];               // (horizontally filtered row) >> 4 for source rows u and u+1
+  auto hrow = [&](int urow, uint32_t (&dst)[NCH]) {
+    const uint32_t r = (uint32_t)min(max(urow, 0), sh - 1);
+    const uint8_t* pa = img + (r * row_bytes + oa);
+    const uint8_t* pb = img + (r * row_bytes + ob);
+    dst[0] = (uint32_t)((int)__ldg(pa) * cx0 + (int)__ldg(pb) * cx1) >> 4;
+    dst[1] = (uint32_t)((int)__ldg(pa + 1) * cx0 + (int)__ldg(pb + 1) * cx1) >> 4;
+    dst[2] = (uint32_t)((int)__ldg(pa + 2) * cx0 + (int)__ldg(pb + 2) * cx1) >> 4;
+    if (HAS_MASK) {
+      const uint8_t* mrow = msk + r * (uint32_t)p.W;
+      dst[3] = (uint32_t)((int)__ldg(mrow + ma) * cx0 + (int)__ldg(mrow + mb) * cx1) >> 4;
+    }
+  };
+
+  int u = s_sy[0];
+  hrow(u, h0);
+  hrow(u + 1, h1);
+  // incremental output addressing
+  const long long plane_sz = (long long)S * S;
+  float* o32 = reinterpret_cast<float*>(p.out) + ((long long)crop * 3 * S + y_begin) * S + x;
+  // engine format: plane (y&1), position (y>>1, x>>1), lane (x&1): consecutive rows alternate planes
+  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                       ((long long)p.g.base + geom_pos(p.g, crop, y_begin >> 1, x >> 1)) * 8 + (x & 1) * 4;
+  const long long o16_plane = p.g.plane * 8;
+  const long long o16_row = (long long)p.g.Wp * 8;
+  for (int y = y_begin; y < y_end; ++y) {
+    const int u_new = s_sy[y - y_begin];
+    if (u_new != u) {
+      if (u_new == u + 1) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) h0[c] = h1[c];
+        hrow(u_new + 1, h1);
+      } else {
+        hrow(u_new, h0);
+        hrow(u_new + 1, h1);
+      }
+      u = u_new;
+    }
+    const uint32_t b0 = s_b0[y - y_begin], b1 = s_b1[y - y_begin];
+    uint32_t v[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) v[c] = (__umulhi(b0, h0[c]) + (__umulhi(b1, h1[c]) + 2u)) >> 2;
+    float f0, f1, f2;
+    const uint32_t m = HAS_MASK ? v[3] : 255u;
+    if (m == 255u) {
+      f0 = s_lut[v[0]]; f1 = s_lut[v[1]]; f2 = s_lut[v[2]];
+    } else if (m == 0u) {
+      f0 = f1 = f2 = 0.f;
+    } else {
+      f0 = normalise_u8((int)v[0], (int)m); f1 = normalise_u8((int)v[1], (int)m); f2 = normalise_u8((int)v[2], (int)m);
+    }
+    if (p.out_fmt == 0) {
+      o32[0] = f0;
+      o32[plane_sz] = f1;
+      o32[2 * plane_sz] = f2;
+      o32 += S;
+    } else {
+      uint2 o;
+      o.x = pack_bf16x2(f0, f1);
+      o.y = pack_bf16x2(f2, 0.f);
+      *reinterpret_cast<uint2*>((y & 1) ? o16 + o16_plane : o16) = o;
+      if (y & 1) o16 += o16_row;
+    }
+  }
+}
+
 template <int TAPS, bool HAS_MASK>
 __global__ void __launch_bounds__(256) roi_crop_kernel(const __grid_constant__ RoiParams p) {
   constexpr int NCH = HAS_MASK ? 4 : 3;
@@ -190,9 +321,7 @@ __global__ void __launch_bounds__(256) roi_crop_kernel(const __grid_constant__ R
     // float32((double(img) * (double(mask)/255.0)) / 255.0) == fp32-rounded (img*mask)/65025 for all
     // 65536 (img,mask) pairs (checked exhaustively in tests/test_oracle_resize.py and on the device)
     const int m = HAS_MASK ? v[3] : 255;
-    const float f0 = __fdiv_rn((float)(v[0] * m), 65025.f);
-    const float f1 = __fdiv_rn((float)(v[1] * m), 65025.f);
-    const float f2 = __fdiv_rn((float)(v[2] * m), 65025.f);
+    const float f0 = normalise_u8(v[0], m), f1 = normalise_u8(v[1], m), f2 = normalise_u8(v[2], m);
     if (p.out_fmt == 0) {
       float* o = reinterpret_cast<float*>(p.out) + ((long long)crop * 3 * S + y) * S + x;
       o[0] = f0;
