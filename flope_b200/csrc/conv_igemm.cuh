@@ -63,14 +63,30 @@ struct ConvParams {
   int res_base, res_Hp, res_Wp;
   // ---- smem ring sizes ----
   int n_a_slots, n_b_slots;
+  // ---- fused 3x3/s2 max-pool (stem only, POOL kernels): one tile = the three conv rows 2i-1..2i+1 of one
+  //      crop, pooled into row i of the output tensor (out_* then describe the pooled grid) ----
+  int pool_rows;               // pooled rows per crop (H/2)
+  int pool_cols;               // pooled columns (W/2)
+  int b_resident;              // all weight tiles fit the ring and n_n_tiles == 1: load them once per CTA
 };
 
-template <int N_TILE, int MT, int KP>
+__host__ __device__ constexpr int pow2_at_least(int v) { int r = 32; while (r < v) r <<= 1; return r; }
+
+// First position of M-tile `m_tile`: consecutive 128*MT-position ranges, or (POOL) the conv rows 2i-1..2i+1.
+template <bool POOL>
+__device__ __forceinline__ int conv_tile_start(const ConvParams& p, int m_tile, int TM) {
+  if (!POOL) return m_tile * TM;
+  const int n = m_tile / p.pool_rows;
+  const int i = m_tile - n * p.pool_rows;
+  return n * (p.Hp * p.Wp) + (2 * i - 1) * p.Wp;
+}
+
+template <int N_TILE, int MT, int KP, bool POOL>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   constexpr int TM = MT * 128;
-  constexpr int ACC_COLS = N_TILE * MT;                         // columns of one accumulator stage
-  constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
-  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
+  constexpr int ACC_COLS = pow2_at_least(N_TILE * MT);          // column stride of one accumulator stage
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static_assert(TMEM_COLS <= 512, "two accumulator stages must fit the 512 TMEM columns");
   constexpr uint32_t IDESC = umma_idesc_bf16(128, N_TILE);
   constexpr int NCHUNK = N_TILE / 32;
   constexpr int KC8 = 2 * KP;                                   // planes per K group
@@ -91,6 +107,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   uint8_t* a_ring = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 512 + (size_t)p.Cout * sizeof(float) + 127) & ~uintptr_t(127));
   uint8_t* b_ring = a_ring + (size_t)p.n_a_slots * a_slot_bytes;
+  // POOL: two staging buffers [N_TILE/8 planes][TM positions][8] bf16 for the post-ReLU conv rows
+  constexpr uint32_t stage_bytes = POOL ? (uint32_t)(N_TILE / 8) * TM * 16u : 0u;
+  uint8_t* pool_stage = b_ring + (size_t)p.n_b_slots * b_tile_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,7 +118,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.n_a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.n_b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], POOL ? kEpiWarps / 2 : kEpiWarps); }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -121,7 +140,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     uint32_t a_phase = 0, b_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_n_tiles;
-      const int tile_start = (tile / p.n_n_tiles) * TM;
+      const int tile_start = conv_tile_start<POOL>(p, tile / p.n_n_tiles, TM);
       const __nv_bfloat16* wtile = p.wgt + (size_t)n_tile * p.taps_total * (b_tile_bytes / 2);
       for (int g = 0; g < p.n_groups; ++g) {
         mbar_wait(&a_empty[a_slot], a_phase ^ 1);
@@ -134,12 +153,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           bulk_g2s_if(leader, a_dst + j * a_plane_bytes, src + (long long)j * p.in_plane * 8, a_plane_bytes, &a_full[a_slot]);
         if (++a_slot == p.n_a_slots) { a_slot = 0; a_phase ^= 1; }
         const int ntaps = p.group_ntaps[g];
-        for (int t = 0; t < ntaps; ++t) {
-          mbar_wait(&b_empty[b_slot], b_phase ^ 1);
-          mbar_expect_tx_if(leader, &b_full[b_slot], b_tile_bytes);
-          bulk_g2s_if(leader, b_ring_addr + b_slot * b_tile_bytes, wtile, b_tile_bytes, &b_full[b_slot]);
-          wtile += b_tile_bytes / 2;
-          if (++b_slot == p.n_b_slots) { b_slot = 0; b_phase ^= 1; }
+        if (!p.b_resident || tile == (int)blockIdx.x) {
+          for (int t = 0; t < ntaps; ++t) {
+            mbar_wait(&b_empty[b_slot], b_phase ^ 1);
+            mbar_expect_tx_if(leader, &b_full[b_slot], b_tile_bytes);
+            bulk_g2s_if(leader, b_ring_addr + b_slot * b_tile_bytes, wtile, b_tile_bytes, &b_full[b_slot]);
+            wtile += b_tile_bytes / 2;
+            if (++b_slot == p.n_b_slots) { b_slot = 0; b_phase ^= 1; }
+          }
         }
       }
     }
@@ -171,7 +192,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const int tofs = p.group_tapofs[g];
         const int ntaps = p.group_ntaps[g];
         for (int t = 0; t < ntaps; ++t) {
-          mbar_wait(&b_full[b_slot], b_phase);
+          if (!p.b_resident || it == 0) mbar_wait(&b_full[b_slot], b_phase);
           tc_fence_after();
           const uint32_t a_tap = a_grp + (uint32_t)p.tap_shift[tofs + t];    // shift in pixels == 16-byte units
           const uint32_t b_tap = b_lo0 + b_slot * b_tile_units;
@@ -182,13 +203,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
               umma_bf16_if(leader, acc + mt * N_TILE, a_tap + k * a_kstep + mt * 128u, desc_hi, b_tap + k * b_kstep, desc_hi,
                            IDESC, (k == 0) ? accumulate : 1u);
           }
-          tc_commit_if(leader, &b_empty[b_slot]);          // frees the weight slot once these MMAs retire
+          if (!p.b_resident) tc_commit_if(leader, &b_empty[b_slot]);   // frees the weight slot once these MMAs retire
           if (t == ntaps - 1) {
             tc_commit_if(leader, &a_empty[a_slot]);
             if (g == p.n_groups - 1) tc_commit_if(leader, &acc_full[stage]);
           }
           accumulate = 1;
-          if (++b_slot == p.n_b_slots) { b_slot = 0; b_phase ^= 1; }
+          if (++b_slot == p.n_b_slots) { b_slot = 0; b_phase ^= (p.b_resident ? 0u : 1u); }
         }
         if (++a_slot == p.n_a_slots) { a_slot = 0; a_phase ^= 1; }
       }
@@ -196,18 +217,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   } else {
     // ===================== epilogue: kEpiWarps warps, 4 per TMEM lane quarter =====================
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read
-    const int sub = (warp - 2) >> 2;       // which share of the (mt, 32-column chunk) list
+    // POOL: the 16 epilogue warps form two groups of 8, one per accumulator stage, so the latency chains
+    // (TMEM load -> stage -> barrier -> pool -> store) of consecutive tiles overlap.
+    const int group = POOL ? (((warp - 2) >> 2) & 1) : 0;
+    const int sub = POOL ? ((warp - 2) >> 3) : ((warp - 2) >> 2);   // share of the (mt, 32-column chunk) list
+    constexpr int NSUB = POOL ? kEpiWarps / 8 : kEpiWarps / 4;
     const int img = p.Hp * p.Wp;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    uint32_t it = POOL ? group : 0;
+    const int tile_step = POOL ? 2 * gridDim.x : gridDim.x;
+    for (int tile = blockIdx.x + (POOL ? group * gridDim.x : 0); tile < total_tiles; tile += tile_step, it += (POOL ? 2 : 1)) {
       const uint32_t stage = it & 1;
       const int n_tile = tile % p.n_n_tiles;
-      const int tile_start = (tile / p.n_n_tiles) * TM;
+      const int tile_start = conv_tile_start<POOL>(p, tile / p.n_n_tiles, TM);
       const int cout_base = n_tile * N_TILE;
+      uint8_t* stage_buf = pool_stage + (it & 1) * stage_bytes;
       const uint32_t acc = tmem_base + stage * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
       bool waited = false;
 #pragma unroll 1
-      for (int c = sub; c < MT * NCHUNK; c += kEpiWarps / 4) {
+      for (int c = sub; c < MT * NCHUNK; c += NSUB) {
         const int mt = c / NCHUNK;
         const int c0 = (c - mt * NCHUNK) * 32;
         const int pos = tile_start + mt * 128 + quarter * 32 + lane;
@@ -215,7 +242,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const int r = pos - n * img;
         const int h = r / p.Wp;
         const int w = r - h * p.Wp;
-        const bool valid = pos < p.n_positions && h < p.H && w < p.W;
+        const bool valid = pos >= 0 && pos < p.n_positions && h < p.H && w < p.W;
         const int plane0 = (cout_base + c0) >> 3;
         uint4 res[4];
         if (p.res != nullptr && valid) {     // issued before the accumulator wait: latency hidden behind the MMAs
@@ -231,13 +258,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         uint32_t v32[32];
         tmem_ld32(acc + (uint32_t)(mt * N_TILE + c0), v32);
         tmem_ld_wait();
-        if (c + kEpiWarps / 4 >= MT * NCHUNK) {
+        if (c + NSUB >= MT * NCHUNK) {
           // this warp's last TMEM read of the stage: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[stage]);
         }
-        if (valid) {
+        if (POOL) {
+          // stage relu(acc + bias) as bf16 (zeros at padded positions: the pool's padding) for the pooling pass
+          const int lp = mt * 128 + quarter * 32 + lane;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (valid) {
+              const float4 ba = *reinterpret_cast<const float4*>(s_bias + cout_base + c0 + j8 * 8);
+              const float4 bb = *reinterpret_cast<const float4*>(s_bias + cout_base + c0 + j8 * 8 + 4);
+              o.x = pack_bf16x2_relu(__uint_as_float(v32[j8 * 8 + 0]) + ba.x, __uint_as_float(v32[j8 * 8 + 1]) + ba.y);
+              o.y = pack_bf16x2_relu(__uint_as_float(v32[j8 * 8 + 2]) + ba.z, __uint_as_float(v32[j8 * 8 + 3]) + ba.w);
+              o.z = pack_bf16x2_relu(__uint_as_float(v32[j8 * 8 + 4]) + bb.x, __uint_as_float(v32[j8 * 8 + 5]) + bb.y);
+              o.w = pack_bf16x2_relu(__uint_as_float(v32[j8 * 8 + 6]) + bb.z, __uint_as_float(v32[j8 * 8 + 7]) + bb.w);
+            }
+            *reinterpret_cast<uint4*>(stage_buf + ((size_t)((c0 >> 3) + j8) * TM + lp) * 16) = o;
+          }
+        } else if (valid) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -284,6 +327,39 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             }
           }
         }
+      }
+      if (POOL) {
+        // all epilogue warps have staged their chunks -> 3x3/s2 max over the three staged conv rows
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kEpiWarps * 16) : "memory");
+        const int m_tile = tile / p.n_n_tiles;
+        const int n = m_tile / p.pool_rows;
+        const int i = m_tile - n * p.pool_rows;
+        const int items = p.pool_cols * (N_TILE / 8);
+        const int gtid = (warp & 3) * 32 + lane + (sub << 7);          // thread index inside the group (0..255)
+        for (int t = gtid; t < items; t += kEpiWarps * 16) {
+          const int plane = t / p.pool_cols;
+          const int j = t - plane * p.pool_cols;
+          const uint8_t* src = stage_buf + (size_t)plane * TM * 16;
+          uint4 m = make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int lr = 0; lr < 3; ++lr) {
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              const int lp = lr * p.Wp + 2 * j + dx;
+              if (lp >= 0) {
+                const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)lp * 16);
+                m.x = bf16x2_max_u32(m.x, v.x); m.y = bf16x2_max_u32(m.y, v.y);
+                m.z = bf16x2_max_u32(m.z, v.z); m.w = bf16x2_max_u32(m.w, v.w);
+              }
+            }
+          }
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                               ((long long)((cout_base >> 3) + plane) * p.out_plane + p.out_base +
+                                ((long long)n * p.out_Hp + i) * p.out_Wp + j) * 8;
+          *reinterpret_cast<uint4*>(dst) = m;
+        }
+        // the group's next tile reuses this staging buffer: everyone must be done reading it
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kEpiWarps * 16) : "memory");
       }
       if (!waited) {
         // a warp with no chunk in this configuration still takes part in the accumulator hand-back

@@ -43,9 +43,9 @@ long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 Geom make_geom(int C, int H, int W, int pad, int max_batch) {
   Geom g;
   g.C = C; g.H = H; g.W = W; g.Hp = H + pad; g.Wp = W + pad;
-  g.base = (int)round_up(2 * g.Wp + 8, 8);
+  g.base = (int)round_up(4 * g.Wp + 8, 8);
   const long long npos = (long long)max_batch * g.Hp * g.Wp;
-  g.plane = g.base + round_up(npos, 1024) + kMaxTM + round_up(2 * g.Wp + 8, 8);
+  g.plane = g.base + round_up(npos, 1024) + kMaxTM + round_up(4 * g.Wp + 8, 8);
   return g;
 }
 
@@ -68,6 +68,7 @@ struct ConvLayer {
   int in_buf, out_buf, res_buf;
   int relu;
   int out_mode;
+  bool pool = false;             // stem only: fused 3x3/s2 max-pool epilogue
   // derived
   int n_tile = 64, mt = 4;
   size_t smem = 0;
@@ -79,27 +80,28 @@ struct ConvLayer {
   float* d_bias = nullptr;
 };
 
-template <int N_TILE, int MT, int KP>
+template <int N_TILE, int MT, int KP, bool POOL>
 cudaError_t conv_set_attr() {
-  return cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, MT, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  return cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, MT, KP, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
 }
-template <int N_TILE, int MT, int KP>
+template <int N_TILE, int MT, int KP, bool POOL>
 void conv_launch_t(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  conv_igemm_kernel<N_TILE, MT, KP><<<grid, kConvThreads, smem, st>>>(p);
+  conv_igemm_kernel<N_TILE, MT, KP, POOL><<<grid, kConvThreads, smem, st>>>(p);
 }
 
-// (N_TILE, MT, KP): output channels per tile, 128-pixel sub-tiles per tile, K=16 MMAs per weight tile
-#define FOR_EACH_CONV_CFG(X) X(64, 4, 4) X(64, 4, 1) X(128, 2, 4)
+// (N_TILE, MT, KP, POOL): output channels per tile, 128-pixel sub-tiles per tile, K=16 MMAs per weight tile,
+// fused 3x3/s2 max-pool epilogue (stem)
+#define FOR_EACH_CONV_CFG(X) X(64, 4, 4, false) X(64, 4, 1, false) X(128, 2, 4, false) X(64, 3, 1, true)
 
 cudaError_t conv_set_all_attrs() {
   cudaError_t e;
-#define X(N, M, K) if ((e = conv_set_attr<N, M, K>()) != cudaSuccess) return e;
+#define X(N, M, K, P) if ((e = conv_set_attr<N, M, K, P>()) != cudaSuccess) return e;
   FOR_EACH_CONV_CFG(X)
 #undef X
   return cudaSuccess;
 }
 bool conv_launch(int n_tile, int mt, const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-#define X(N, M, K) if (n_tile == N && mt == M && p.kc8 == 2 * K) { conv_launch_t<N, M, K>(p, grid, smem, st); return true; }
+#define X(N, M, K, P) if (n_tile == N && mt == M && p.kc8 == 2 * K && (p.pool_rows > 0) == P) { conv_launch_t<N, M, K, P>(p, grid, smem, st); return true; }
   FOR_EACH_CONV_CFG(X)
 #undef X
   return false;
@@ -114,6 +116,9 @@ struct flope_engine {
   std::vector<ActBuf> bufs;
   std::map<std::string, int> act_names;          // debug name -> buffer index
   std::vector<ConvLayer> layers;
+  ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
+  bool fuse_pool = false;                        // opt-in (flope_debug_set "fuse_pool"): measured no faster than stem + maxpool kernels
+  bool can_fuse_pool = false;
   int buf_x0 = -1, buf_stem = -1, buf_pool_in = -1, buf_pool = -1, buf_mp_out = -1;
   float* d_feat = nullptr;                       // (max_batch, 2048) fp32
   float* d_wrot = nullptr;                       // (9, 2048) fp32
@@ -277,10 +282,18 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
   // ---- tile configuration: persistent kernel, one CTA per SM, accumulator double-buffered in TMEM ----
   L.n_tile = L.cout >= 128 ? 128 : 64;
   L.mt = 256 / L.n_tile;                       // 2 stages x 256 columns = all 512 TMEM columns
+  size_t pool_smem = 0;
+  if (L.pool) {
+    L.mt = 3;                                  // three conv rows of Wp positions per tile
+    if (3 * p.Wp > L.mt * 128) return fail(FLOPE_EINVAL, "fused stem pooling needs 3*(S/2+2) <= 384 (crop side <= 252)");
+    p.pool_rows = p.H / 2;
+    p.pool_cols = p.W / 2;
+    pool_smem = (size_t)2 * (L.n_tile / 8) * (L.mt * 128) * 16;
+  }
   const int halo = p.halo_before + p.halo_after;
   auto smem_of = [&](int n_a, int n_b) {
     return (size_t)1024 + (size_t)L.cout * sizeof(float) + (size_t)n_a * p.kc8 * (L.mt * 128 + halo) * 16 +
-           (size_t)n_b * p.kc8 * L.n_tile * 16;
+           (size_t)n_b * p.kc8 * L.n_tile * 16 + pool_smem;
   };
   // weight tiles are consumed every MT*kc8/2 MMAs, so several must be in flight to cover L2 latency;
   // halo tiles are consumed once per group: two or three slots are enough.  Rings run across tiles.
@@ -293,6 +306,8 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
   }
   if (!best_a) return fail(FLOPE_EINVAL, "conv layer " + L.name + " does not fit in shared memory");
   p.n_a_slots = best_a; p.n_b_slots = best_b;
+  p.b_resident = (L.cout == L.n_tile && p.taps_total <= best_b) ? 1 : 0;   // e.g. stem: all 16 weight tiles stay in smem
+  if (p.b_resident) p.n_b_slots = p.taps_total;                            // slot t <-> weight tile t, for every tile
   L.smem = smem_of(best_a, best_b);
   return FLOPE_OK;
 }
@@ -305,6 +320,12 @@ int build_network(flope_engine* e) {
   int cur = add_buf(e, 64, s4, s4, 1, false, "maxpool");
   e->buf_mp_out = cur;
   add_conv(e, "conv1", K_STEM, 16, 64, e->buf_x0, e->buf_stem, -1, 1, OUT_PLAIN, "base.conv1.weight", "base.bn1");
+  if (3 * (s2 + 2) <= 384) {                   // fused stem + max-pool (crop side <= 252); larger crops keep two kernels
+    ConvLayer L = e->layers.back();
+    L.name = "conv1+maxpool"; L.out_buf = e->buf_mp_out; L.pool = true;
+    e->stem_pool = L;
+    e->can_fuse_pool = true;
+  }
   int C = 64, side = s4;
   for (int stage = 1; stage <= 4; ++stage) {
     const std::string ln = "base.layer" + std::to_string(stage);
@@ -408,7 +429,7 @@ int run_conv(flope_engine* e, ConvLayer& L, int n, cudaStream_t st) {
   p.n_positions = n * p.Hp * p.Wp;
   p.wgt = L.d_w; p.bias = L.d_bias;
   const int TM = L.mt * 128;
-  p.n_m_tiles = (p.n_positions + TM - 1) / TM;
+  p.n_m_tiles = L.pool ? n * p.pool_rows : (p.n_positions + TM - 1) / TM;
   p.n_n_tiles = L.cout / L.n_tile;
   dim3 grid((unsigned)std::min(p.n_m_tiles * p.n_n_tiles, e->num_sms));
   if (!conv_launch(L.n_tile, L.mt, p, grid, L.smem, st)) return fail(FLOPE_EINVAL, "no kernel instance for " + L.name);
@@ -425,8 +446,11 @@ int grid_for(long long total, int block) {
 int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
   int rc;
   size_t li = 0;
-  if ((rc = run_conv(e, e->layers[li++], n, st))) return rc;       // stem
-  {
+  if (e->fuse_pool) {
+    ++li;
+    if ((rc = run_conv(e, e->stem_pool, n, st))) return rc;        // stem conv + BN + ReLU + max-pool in one kernel
+  } else {
+    if ((rc = run_conv(e, e->layers[li++], n, st))) return rc;     // stem
     const ActBuf& a = e->bufs[e->buf_stem];
     const ActBuf& b = e->bufs[e->buf_mp_out];
     const long long total = (long long)(a.g.C / 8) * n * b.g.H * b.g.W;
@@ -568,6 +592,7 @@ int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_
   CUDA_TRY(cudaMalloc(&e->d_r9, (size_t)e->max_batch * 9 * sizeof(float)));
   for (ConvLayer& L : e->layers)
     if ((rc = plan_conv(e, L))) { flope_engine_destroy(e); return rc; }
+  if (e->can_fuse_pool && (rc = plan_conv(e, e->stem_pool))) { flope_engine_destroy(e); return rc; }
   CUDA_TRY(cudaDeviceSynchronize());
   *out = e;
   return FLOPE_OK;
@@ -580,6 +605,7 @@ void flope_engine_destroy(flope_engine* e) {
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (ActBuf& b : e->bufs) cudaFree(b.d);
   for (ConvLayer& L : e->layers) { cudaFree(L.d_w); cudaFree(L.d_scale); cudaFree(L.d_bias); }
+  cudaFree(e->stem_pool.d_w); cudaFree(e->stem_pool.d_scale); cudaFree(e->stem_pool.d_bias);
   cudaFree(e->d_feat); cudaFree(e->d_wrot); cudaFree(e->d_brot); cudaFree(e->d_r9);
   delete e;
 }
@@ -598,7 +624,11 @@ int flope_engine_load_weights(flope_engine* e, const flope_tensor_desc* tensors,
     for (int d = 0; d < it->second->ndim; ++d) ne *= it->second->shape[d];
     return ne == numel ? it->second->data : nullptr;
   };
-  for (ConvLayer& L : e->layers) {
+  std::vector<ConvLayer*> all;
+  for (ConvLayer& L : e->layers) all.push_back(&L);
+  if (e->can_fuse_pool) all.push_back(&e->stem_pool);
+  for (ConvLayer* Lp : all) {
+    ConvLayer& L = *Lp;
     int64_t wn = 0;
     switch (L.kind) {
       case K_CONV3: case K_CONV3_S2: wn = (int64_t)L.cout * L.cin * 9; break;
@@ -797,6 +827,12 @@ int flope_debug_normalise_lut(float* d_out, void* stream) {
 int flope_debug_set(flope_engine* e, const char* key, int value) {
   if (!e || !key) return fail(FLOPE_EINVAL, "NULL argument");
   if (!std::strcmp(key, "use_graph")) { e->use_graph = value != 0; return FLOPE_OK; }
+  if (!std::strcmp(key, "fuse_pool")) {
+    if (value && !e->can_fuse_pool) return fail(FLOPE_EINVAL, "fused stem pooling supports crop sides up to 252");
+    e->fuse_pool = value != 0;
+    drop_graphs(e);
+    return FLOPE_OK;
+  }
   return fail(FLOPE_EINVAL, std::string("unknown debug key ") + key);
 }
 

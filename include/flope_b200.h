@@ -114,7 +114,8 @@ int flope_engine_profile_read(flope_engine* e, char* names, int names_len, float
 int64_t flope_debug_activation(flope_engine* e, const char* name, int n, float* d_out, void* stream);
 /* Evaluate the device mask/normalise arithmetic for all (mask,img) uint8 pairs: d_out (256,256) f32. */
 int flope_debug_normalise_lut(float* d_out, void* stream);
-/* Set a named option: "use_graph" = 0/1 (replay the backbone as a CUDA graph; default 1). */
+/* Set a named option: "use_graph" = 0/1 (replay the backbone as a CUDA graph; default 1);
+ * "fuse_pool" = 0/1 (stem conv + max-pool as one kernel instead of two; default 0, crop side <= 252). */
 int flope_debug_set(flope_engine* e, const char* key, int value);
 
 #ifdef __cplusplus

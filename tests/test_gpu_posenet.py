@@ -38,17 +38,39 @@ def _rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm())
 
 
-def test_every_block_matches_oracle(eng224, net):
+@pytest.mark.parametrize("fuse_pool", [0, 1])
+def test_every_block_matches_oracle(eng224, net, fuse_pool):
+    """fuse_pool=0 is the default path (stem kernel + max-pool kernel); fuse_pool=1 is the opt-in single kernel
+    (stem conv + BN + ReLU + max-pool, no stem tensor in HBM), which must give the same tensors."""
     x = synth.mixed_crops(6, 224)
     acts = onet.trunk_activations(net, x)
-    r9 = eng224.posenet_forward(x.cuda())
-    torch.cuda.synchronize()
-    for name in BLOCKS:
-        buf, chw = eng224.debug_activation(name, x.shape[0])
+    eng224.debug_set("fuse_pool", fuse_pool)
+    try:
+        r9 = eng224.posenet_forward(x.cuda())
         torch.cuda.synchronize()
-        got = buf.cpu().reshape(acts[name].shape)
-        assert _rel(got, acts[name]) < 2e-2, name
-    assert _rel(r9.cpu(), acts["r9"]) < 2e-2
+        for name in BLOCKS[1 if fuse_pool else 0:]:
+            buf, chw = eng224.debug_activation(name, x.shape[0])
+            torch.cuda.synchronize()
+            got = buf.cpu().reshape(acts[name].shape)
+            assert _rel(got, acts[name]) < 2e-2, name
+        assert _rel(r9.cpu(), acts["r9"]) < 2e-2
+    finally:
+        eng224.debug_set("fuse_pool", 0)
+
+
+def test_fused_and_unfused_stem_agree_bitwise(eng224):
+    x = synth.mixed_crops(9, 224).cuda()
+    eng224.debug_set("fuse_pool", 0)
+    a = eng224.posenet_forward(x).clone()
+    pa, _ = eng224.debug_activation("maxpool", 9)
+    pa = pa.clone()
+    eng224.debug_set("fuse_pool", 1)
+    b = eng224.posenet_forward(x).clone()
+    pb, _ = eng224.debug_activation("maxpool", 9)
+    torch.cuda.synchronize()
+    eng224.debug_set("fuse_pool", 0)
+    assert torch.equal(pa, pb)
+    assert torch.equal(a, b)
 
 
 def test_orientation_within_half_degree_mean(eng224, net):
