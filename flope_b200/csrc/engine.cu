@@ -533,9 +533,15 @@ int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W
     rp.out = d_out;
   }
   rp.rows_per_strip = S >= 448 ? 128 : 112;
-  const int block = S >= 256 ? 256 : ((S + 31) / 32 * 32);
+  int block = S >= 256 ? 256 : ((S + 31) / 32 * 32);
   dim3 grid((S + block - 1) / block, (S + rp.rows_per_strip - 1) / rp.rows_per_strip, n);
   const bool has_mask = d_masks != nullptr;
+  if (interp != FLOPE_INTERP_LANCZOS4) {           // bilinear kernel: one thread per column pair
+    const int cols = S / 2;
+    block = cols >= 256 ? 256 : ((cols + 31) / 32 * 32);
+    rp.rows_per_strip = S >= 448 ? 128 : 56;
+    grid = dim3((cols + block - 1) / block, (S + rp.rows_per_strip - 1) / rp.rows_per_strip, n);
+  }
   ProfScope ps(e, "roi_crop", st);
   if (interp == FLOPE_INTERP_LANCZOS4) {
     if (has_mask) roi_crop_kernel<8, true><<<grid, block, 0, st>>>(rp);
