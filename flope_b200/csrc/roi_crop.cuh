@@ -105,7 +105,10 @@ __device__ __forceinline__ float normalise_u8(int img, int mask) {
 //   ((b*(S>>4))>>16) == mulhi(b<<16, S>>4).   The result never leaves [0,255], so no saturation is needed.
 // ---------------------------------------------------------------------------------------------
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(256, 7) roi_bilinear_kernel(const __grid_constant__ RoiParams p) {
+__global__ void __launch_bounds__(256) roi_bilinear_kernel(const __grid_constant__ RoiParams p) {
+  // thread = two adjacent output columns (2q, 2q+1) marching down the strip: one thread produces both
+  // 16-byte halves of a space-to-depth stem pixel, and the row bookkeeping / coefficient fetches are
+  // shared by the two columns.
   constexpr int NCH = HAS_MASK ? 4 : 3;
   __shared__ int s_sy[kRoiMaxStripRows];
   __shared__ uint32_t s_b0[kRoiMaxStripRows];
@@ -117,9 +120,9 @@ __global__ void __launch_bounds__(256, 7) roi_bilinear_kernel(const __grid_const
   const int frame = bx[0], xmin = bx[1], ymin = bx[2];
   const int sw = bx[3] - bx[1], sh = bx[4] - bx[2];
   const int S = p.S;
-  const int y_begin = blockIdx.y * p.rows_per_strip;
+  const int y_begin = blockIdx.y * p.rows_per_strip;           // even
   const int y_end = min(S, y_begin + p.rows_per_strip);
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (sw <= 0 || sh <= 0) return;
 
   const double scale_x = 1.0 / ((double)S / (double)sw);
@@ -134,46 +137,50 @@ __global__ void __launch_bounds__(256, 7) roi_bilinear_kernel(const __grid_const
   }
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = normalise_u8(i, 255);
   __syncthreads();
-  if (x >= S) return;
+  if (2 * q >= S) return;
 
-  int cx0, cx1;
-  uint32_t oa, ob, ma, mb;                 // 32-bit byte offsets of the two horizontal taps inside the crop
-  {
+  int cx0[2], cx1[2];
+  uint32_t oa[2], ob[2];                   // source columns of the two horizontal taps of each output column
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
     short ic[2];
     int sx;
-    linear_coefs(x, scale_x, sw, false, sx, ic);
-    const int x0 = min(max(sx, 0), sw - 1);
-    const int x1 = min(max(sx + 1, 0), sw - 1);
-    cx0 = ic[0]; cx1 = ic[1];
-    oa = x0 * 3; ob = x1 * 3; ma = x0; mb = x1;
+    linear_coefs(2 * q + k, scale_x, sw, false, sx, ic);
+    cx0[k] = ic[0]; cx1[k] = ic[1];
+    oa[k] = (uint32_t)min(max(sx, 0), sw - 1);
+    ob[k] = (uint32_t)min(max(sx + 1, 0), sw - 1);
   }
   const uint8_t* img = p.frames + (long long)frame * p.frame_stride + ((long long)ymin * p.W + xmin) * 3;
   const uint8_t* msk = HAS_MASK ? p.masks + (long long)frame * p.mask_stride + (long long)ymin * p.W + xmin : nullptr;
   const uint32_t row_bytes = (uint32_t)p.W * 3u;
 
-  uint32_t h0[NCH], h1[NCH];               // (horizontally filtered row) >> 4 for source rows u and u+1
-  auto hrow = [&](int urow, uint32_t (&dst)[NCH]) {
+  uint32_t h0[2][NCH], h1[2][NCH];         // (horizontally filtered row) >> 4 for source rows u and u+1, per column
+  auto hrow = [&](int urow, uint32_t (&dst)[2][NCH]) {
     const uint32_t r = (uint32_t)min(max(urow, 0), sh - 1);
-    const uint8_t* pa = img + (r * row_bytes + oa);
-    const uint8_t* pb = img + (r * row_bytes + ob);
-    dst[0] = (uint32_t)((int)__ldg(pa) * cx0 + (int)__ldg(pb) * cx1) >> 4;
-    dst[1] = (uint32_t)((int)__ldg(pa + 1) * cx0 + (int)__ldg(pb + 1) * cx1) >> 4;
-    dst[2] = (uint32_t)((int)__ldg(pa + 2) * cx0 + (int)__ldg(pb + 2) * cx1) >> 4;
+    const uint8_t* row = img + r * row_bytes;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint8_t* pa = row + oa[k] * 3u;
+      const uint8_t* pb = row + ob[k] * 3u;
+      dst[k][0] = (uint32_t)((int)__ldg(pa) * cx0[k] + (int)__ldg(pb) * cx1[k]) >> 4;
+      dst[k][1] = (uint32_t)((int)__ldg(pa + 1) * cx0[k] + (int)__ldg(pb + 1) * cx1[k]) >> 4;
+      dst[k][2] = (uint32_t)((int)__ldg(pa + 2) * cx0[k] + (int)__ldg(pb + 2) * cx1[k]) >> 4;
+    }
     if (HAS_MASK) {
       const uint8_t* mrow = msk + r * (uint32_t)p.W;
-      dst[3] = (uint32_t)((int)__ldg(mrow + ma) * cx0 + (int)__ldg(mrow + mb) * cx1) >> 4;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        dst[k][3] = (uint32_t)((int)__ldg(mrow + oa[k]) * cx0[k] + (int)__ldg(mrow + ob[k]) * cx1[k]) >> 4;
     }
   };
 
   int u = s_sy[0];
   hrow(u, h0);
   hrow(u + 1, h1);
-  // incremental output addressing
   const long long plane_sz = (long long)S * S;
-  float* o32 = reinterpret_cast<float*>(p.out) + ((long long)crop * 3 * S + y_begin) * S + x;
-  // engine format: plane (y&1), position (y>>1, x>>1), lane (x&1): consecutive rows alternate planes
+  float* o32 = reinterpret_cast<float*>(p.out) + ((long long)crop * 3 * S + y_begin) * S + 2 * q;
   __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                       ((long long)p.g.base + geom_pos(p.g, crop, y_begin >> 1, x >> 1)) * 8 + (x & 1) * 4;
+                       ((long long)p.g.base + geom_pos(p.g, crop, y_begin >> 1, q)) * 8;
   const long long o16_plane = p.g.plane * 8;
   const long long o16_row = (long long)p.g.Wp * 8;
   for (int y = y_begin; y < y_end; ++y) {
@@ -181,7 +188,9 @@ __global__ void __launch_bounds__(256, 7) roi_bilinear_kernel(const __grid_const
     if (u_new != u) {
       if (u_new == u + 1) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) h0[c] = h1[c];
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) h0[k][c] = h1[k][c];
         hrow(u_new + 1, h1);
       } else {
         hrow(u_new, h0);
@@ -190,28 +199,32 @@ __global__ void __launch_bounds__(256, 7) roi_bilinear_kernel(const __grid_const
       u = u_new;
     }
     const uint32_t b0 = s_b0[y - y_begin], b1 = s_b1[y - y_begin];
-    uint32_t v[NCH];
+    float f[2][3];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) v[c] = (__umulhi(b0, h0[c]) + (__umulhi(b1, h1[c]) + 2u)) >> 2;
-    float f0, f1, f2;
-    const uint32_t m = HAS_MASK ? v[3] : 255u;
-    if (m == 255u) {
-      f0 = s_lut[v[0]]; f1 = s_lut[v[1]]; f2 = s_lut[v[2]];
-    } else if (m == 0u) {
-      f0 = f1 = f2 = 0.f;
-    } else {
-      f0 = normalise_u8((int)v[0], (int)m); f1 = normalise_u8((int)v[1], (int)m); f2 = normalise_u8((int)v[2], (int)m);
+    for (int k = 0; k < 2; ++k) {
+      uint32_t v[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) v[c] = (__umulhi(b0, h0[k][c]) + (__umulhi(b1, h1[k][c]) + 2u)) >> 2;
+      const uint32_t m = HAS_MASK ? v[3] : 255u;
+      if (m == 255u) {
+        f[k][0] = s_lut[v[0]]; f[k][1] = s_lut[v[1]]; f[k][2] = s_lut[v[2]];
+      } else if (m == 0u) {
+        f[k][0] = f[k][1] = f[k][2] = 0.f;
+      } else {
+        f[k][0] = normalise_u8((int)v[0], (int)m); f[k][1] = normalise_u8((int)v[1], (int)m);
+        f[k][2] = normalise_u8((int)v[2], (int)m);
+      }
     }
     if (p.out_fmt == 0) {
-      o32[0] = f0;
-      o32[plane_sz] = f1;
-      o32[2 * plane_sz] = f2;
+      *reinterpret_cast<float2*>(o32) = make_float2(f[0][0], f[1][0]);
+      *reinterpret_cast<float2*>(o32 + plane_sz) = make_float2(f[0][1], f[1][1]);
+      *reinterpret_cast<float2*>(o32 + 2 * plane_sz) = make_float2(f[0][2], f[1][2]);
       o32 += S;
     } else {
-      uint2 o;
-      o.x = pack_bf16x2(f0, f1);
-      o.y = pack_bf16x2(f2, 0.f);
-      *reinterpret_cast<uint2*>((y & 1) ? o16 + o16_plane : o16) = o;
+      uint4 o;
+      o.x = pack_bf16x2(f[0][0], f[0][1]); o.y = pack_bf16x2(f[0][2], 0.f);
+      o.z = pack_bf16x2(f[1][0], f[1][1]); o.w = pack_bf16x2(f[1][2], 0.f);
+      *reinterpret_cast<uint4*>((y & 1) ? o16 + o16_plane : o16) = o;
       if (y & 1) o16 += o16_row;
     }
   }
