@@ -68,6 +68,12 @@ struct ConvParams {
   int pool_rows;               // pooled rows per crop (H/2)
   int pool_cols;               // pooled columns (W/2)
   int b_resident;              // all weight tiles fit the ring and n_n_tiles == 1: load them once per CTA
+  // ---- second A source: K groups >= first_group2 are read from in2 (the projection shortcut of a
+  //      ResNet block folded into its conv2 as extra K: same position space, shift 0) ----
+  const __nv_bfloat16* in2;
+  long long in2_plane;
+  int in2_base;
+  int first_group2;            // == n_groups when there is no second source
 };
 
 __host__ __device__ constexpr int pow2_at_least(int v) { int r = 32; while (r < v) r <<= 1; return r; }
@@ -146,11 +152,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         mbar_wait(&a_empty[a_slot], a_phase ^ 1);
         mbar_expect_tx_if(leader, &a_full[a_slot], a_slot_bytes);
         const uint32_t a_dst = a_ring_addr + a_slot * a_slot_bytes;
-        const __nv_bfloat16* src =
-            p.in + ((long long)p.group_plane[g] * p.in_plane + p.in_base + tile_start - p.halo_before) * 8;
+        const bool second = g >= p.first_group2;
+        const long long a_plane = second ? p.in2_plane : p.in_plane;
+        const __nv_bfloat16* src = (second ? p.in2 : p.in) +
+            ((long long)p.group_plane[g] * a_plane + (second ? p.in2_base : p.in_base) + tile_start - p.halo_before) * 8;
 #pragma unroll
         for (int j = 0; j < KC8; ++j)
-          bulk_g2s_if(leader, a_dst + j * a_plane_bytes, src + (long long)j * p.in_plane * 8, a_plane_bytes, &a_full[a_slot]);
+          bulk_g2s_if(leader, a_dst + j * a_plane_bytes, src + (long long)j * a_plane * 8, a_plane_bytes, &a_full[a_slot]);
         if (++a_slot == p.n_a_slots) { a_slot = 0; a_phase ^= 1; }
         const int ntaps = p.group_ntaps[g];
         if (!p.b_resident || tile == (int)blockIdx.x) {

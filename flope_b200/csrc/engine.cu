@@ -69,6 +69,9 @@ struct ConvLayer {
   int relu;
   int out_mode;
   bool pool = false;             // stem only: fused 3x3/s2 max-pool epilogue
+  // projection shortcut folded into this conv as extra K groups (block 0 of layers 2-4):
+  int short_buf = -1, cin2 = 0;
+  std::string wkey2, bnkey2;
   // derived
   int n_tile = 64, mt = 4;
   size_t smem = 0;
@@ -187,6 +190,21 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
         L.group_cin.push_back(g * 64);
       }
       p.halo_before = Wp + 1; p.halo_after = Wp + 1;
+      p.first_group2 = p.n_groups;
+      if (L.short_buf >= 0) {
+        // out = relu(bn2(conv2(t)) + bn_d(conv1x1_s2(x))): with both BN scales folded into the weights the 1x1
+        // stride-2 projection is just more K for the same accumulator.  x lives parity-split; its (0,0)
+        // sub-grid (planes 0 .. cin2/8-1) is indexed by the same positions as t, shift 0 = tap entry 4.
+        const ActBuf& sb = e->bufs[L.short_buf];
+        if (sb.g.Hp != in.g.Hp || sb.g.Wp != in.g.Wp) return fail(FLOPE_EINVAL, "shortcut geometry mismatch");
+        p.in2 = sb.d; p.in2_plane = sb.g.plane; p.in2_base = sb.g.base;
+        for (int c = 0; c < L.cin2 / 64; ++c) {
+          const int g = p.n_groups++;
+          p.group_plane[g] = c * 8; p.group_tapofs[g] = 4; p.group_ntaps[g] = 1;
+          L.group_taps.push_back({{1, 1}});
+          L.group_cin.push_back(c * 64);
+        }
+      }
       break;
     }
     case K_CONV3_S2: {   // input is parity-split; its Geom is the half-resolution (= output) grid
@@ -258,6 +276,7 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
       break;
     }
   }
+  if (L.kind != K_CONV3) p.first_group2 = p.n_groups;
   if (p.n_groups > kMaxGroups || ntap_entries > kMaxTaps) return fail(FLOPE_EINVAL, "conv plan exceeds table sizes");
   p.taps_total = 0;
   for (int g = 0; g < p.n_groups; ++g) p.taps_total += p.group_ntaps[g];
@@ -339,12 +358,14 @@ int build_network(flope_engine* e) {
     } else {
       // `cur` is the parity-split output of the previous stage, geometry = this stage's grid
       const int cin = C / 2;
-      int bufD = add_buf(e, C, side, side, 1, false, nullptr);
       blk0_out = add_buf(e, C, side, side, 1, false, (dn + ".0").c_str());
       add_conv(e, dn + ".0.conv1", K_CONV3_S2, cin, C, cur, bufB, -1, 1, OUT_PLAIN, ln + ".0.conv1.weight", ln + ".0.bn1");
-      add_conv(e, dn + ".0.downsample", K_DOWN1_S2, cin, C, cur, bufD, -1, 0, OUT_PLAIN, ln + ".0.downsample.0.weight",
-               ln + ".0.downsample.1");
-      add_conv(e, dn + ".0.conv2", K_CONV3, C, C, bufB, blk0_out, bufD, 1, OUT_PLAIN, ln + ".0.conv2.weight", ln + ".0.bn2");
+      // conv2 + the 1x1/s2 projection shortcut (downsample.0 / downsample.1) in one accumulator
+      add_conv(e, dn + ".0.conv2+downsample", K_CONV3, C, C, bufB, blk0_out, -1, 1, OUT_PLAIN, ln + ".0.conv2.weight", ln + ".0.bn2");
+      e->layers.back().short_buf = cur;
+      e->layers.back().cin2 = cin;
+      e->layers.back().wkey2 = ln + ".0.downsample.0.weight";
+      e->layers.back().bnkey2 = ln + ".0.downsample.1";
     }
     int blk1_out;
     int mode;
@@ -366,7 +387,8 @@ int build_network(flope_engine* e) {
   return FLOPE_OK;
 }
 
-void pack_weights_host(const ConvLayer& L, const float* w, const std::vector<float>& scale, std::vector<__nv_bfloat16>& out) {
+void pack_weights_host(const ConvLayer& L, const float* w, const std::vector<float>& scale, const float* w2,
+                       const std::vector<float>& scale2, std::vector<__nv_bfloat16>& out) {
   const ConvParams& p = L.p;
   const int NT = L.n_tile;
   const int n_tiles = L.cout / NT;
@@ -383,6 +405,11 @@ void pack_weights_host(const ConvLayer& L, const float* w, const std::vector<flo
             for (int j = 0; j < 8; ++j) {
               const int co = nt * NT + n;
               float v = 0.f;
+              if (g >= p.first_group2) {          // projection shortcut: (Cout, Cin2) 1x1 weights, their own BN scale
+                const int ci = L.group_cin[g] + k8 * 8 + j;
+                dst[((size_t)k8 * NT + n) * 8 + j] = __float2bfloat16_rn(w2[(size_t)co * L.cin2 + ci] * scale2[co]);
+                continue;
+              }
               switch (L.kind) {
                 case K_CONV3:
                 case K_CONV3_S2: {
@@ -660,8 +687,23 @@ int flope_engine_load_weights(flope_engine* e, const flope_tensor_desc* tensors,
       if (!b) return fail(FLOPE_EINVAL, "bias missing: " + L.biaskey);
       for (int c = 0; c < L.cout; ++c) bias[c] = b[c];
     }
+    const float* w2 = nullptr;
+    std::vector<float> scale2(L.cout, 1.f);
+    if (L.short_buf >= 0) {
+      w2 = need(L.wkey2, (int64_t)L.cout * L.cin2);
+      const float* gw = need(L.bnkey2 + ".weight", L.cout);
+      const float* gb = need(L.bnkey2 + ".bias", L.cout);
+      const float* mu = need(L.bnkey2 + ".running_mean", L.cout);
+      const float* var = need(L.bnkey2 + ".running_var", L.cout);
+      if (!w2 || !gw || !gb || !mu || !var) return fail(FLOPE_EINVAL, "projection shortcut entries missing: " + L.wkey2);
+      for (int c = 0; c < L.cout; ++c) {
+        const float s2 = gw[c] / std::sqrt(var[c] + 1e-5f);
+        scale2[c] = s2;
+        bias[c] += gb[c] - mu[c] * s2;        // one fp32 bias for the summed branches
+      }
+    }
     std::vector<__nv_bfloat16> packed;
-    pack_weights_host(L, w, scale, packed);
+    pack_weights_host(L, w, scale, w2, scale2, packed);
     cudaFree(L.d_w); cudaFree(L.d_scale); cudaFree(L.d_bias);
     L.d_w = nullptr; L.d_scale = nullptr; L.d_bias = nullptr;
     CUDA_TRY(cudaMalloc(&L.d_w, packed.size() * sizeof(__nv_bfloat16)));
