@@ -87,13 +87,24 @@ __device__ __forceinline__ int conv_tile_start(const ConvParams& p, int m_tile, 
   return n * (p.Hp * p.Wp) + (2 * i - 1) * p.Wp;
 }
 
-template <int N_TILE, int MT, int KP, bool POOL>
+// PAIR: the kernel is launched as clusters of two CTAs (one TPC).  A pair tile is 2*TM positions x N_TILE
+// channels: CTA r owns positions [r*TM, (r+1)*TM) of it (its own A halo tiles, accumulators and epilogue) and
+// loads rows [r*N_TILE/2, (r+1)*N_TILE/2) of every weight tile; the leader CTA (rank 0) issues
+// tcgen05.mma.cta_group::2 (M = 256) for both.  Per SM and per MMA the shared-memory port then serves
+// 128 A rows + N_TILE/2 B rows instead of 128 + N_TILE, which is what bounds the single-CTA kernel.
+//   full barriers : each CTA's TMA completes on its own barrier; rank 1's warp 1 relays every completed phase to
+//                   the leader's barrier (count 2 there: local producer + relay)
+//   empty barriers: tcgen05.commit multicast arrives in both CTAs
+//   accumulator   : acc_full by multicast commit; acc_empty lives in the leader (both CTAs' epilogue warps arrive)
+template <int N_TILE, int MT, int KP, bool POOL, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(!(POOL && PAIR), "the fused-pool epilogue is single-CTA only");
   constexpr int TM = MT * 128;
+  constexpr int NB_ROWS = PAIR ? N_TILE / 2 : N_TILE;            // weight rows this CTA holds per tile
   constexpr int ACC_COLS = pow2_at_least(N_TILE * MT);          // column stride of one accumulator stage
   constexpr int TMEM_COLS = 2 * ACC_COLS;
   static_assert(TMEM_COLS <= 512, "two accumulator stages must fit the 512 TMEM columns");
-  constexpr uint32_t IDESC = umma_idesc_bf16(128, N_TILE);
+  constexpr uint32_t IDESC = umma_idesc_bf16(PAIR ? 256 : 128, N_TILE);
   constexpr int NCHUNK = N_TILE / 32;
   constexpr int KC8 = 2 * KP;                                   // planes per K group
 
@@ -109,7 +120,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   const int halo = p.halo_before + p.halo_after;
   const uint32_t a_plane_bytes = (uint32_t)(TM + halo) * 16u;
   const uint32_t a_slot_bytes = a_plane_bytes * KC8;
-  constexpr uint32_t b_tile_bytes = (uint32_t)KC8 * N_TILE * 16u;
+  constexpr uint32_t b_tile_bytes = (uint32_t)KC8 * NB_ROWS * 16u;
   uint8_t* a_ring = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 512 + (size_t)p.Cout * sizeof(float) + 127) & ~uintptr_t(127));
   uint8_t* b_ring = a_ring + (size_t)p.n_a_slots * a_slot_bytes;
@@ -120,20 +131,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.n_m_tiles * p.n_n_tiles;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader (issues the MMAs)
+  const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tiles are dealt to pairs (or CTAs) round-robin
+  const int tile_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int rank_ofs = PAIR ? (int)rank * TM : 0;                // this CTA's first position inside a pair tile
+  constexpr int TILE_POS = PAIR ? 2 * TM : TM;                   // positions per (pair) tile
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.n_a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.n_b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], POOL ? kEpiWarps / 2 : kEpiWarps); }
+    const uint32_t full_count = (PAIR && rank == 0) ? 2u : 1u;   // leader: own producer + the peer's relay
+    for (int i = 0; i < p.n_a_slots; ++i) { mbar_init(&a_full[i], full_count); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.n_b_slots; ++i) { mbar_init(&b_full[i], full_count); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], POOL ? kEpiWarps / 2 : (PAIR ? 2 * kEpiWarps : kEpiWarps));
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc2(tmem_ptr, TMEM_COLS); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_ptr, TMEM_COLS); tmem_relinquish(); }
   }
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -144,10 +165,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const uint32_t b_ring_addr = smem_u32(b_ring);
     int a_slot = 0, b_slot = 0;
     uint32_t a_phase = 0, b_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
       const int n_tile = tile % p.n_n_tiles;
-      const int tile_start = conv_tile_start<POOL>(p, tile / p.n_n_tiles, TM);
-      const __nv_bfloat16* wtile = p.wgt + (size_t)n_tile * p.taps_total * (b_tile_bytes / 2);
+      const int tile_start = conv_tile_start<POOL>(p, tile / p.n_n_tiles, TILE_POS) + rank_ofs;
+      // PAIR: weights are packed [n_tile][tile][rank][k8][N_TILE/2][8], so each CTA's half is one contiguous copy
+      const __nv_bfloat16* wtile = p.wgt + ((size_t)n_tile * p.taps_total * (PAIR ? 2 : 1) + rank) * (b_tile_bytes / 2);
       for (int g = 0; g < p.n_groups; ++g) {
         mbar_wait(&a_empty[a_slot], a_phase ^ 1);
         mbar_expect_tx_if(leader, &a_full[a_slot], a_slot_bytes);
@@ -161,15 +183,39 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           bulk_g2s_if(leader, a_dst + j * a_plane_bytes, src + (long long)j * a_plane * 8, a_plane_bytes, &a_full[a_slot]);
         if (++a_slot == p.n_a_slots) { a_slot = 0; a_phase ^= 1; }
         const int ntaps = p.group_ntaps[g];
-        if (!p.b_resident || tile == (int)blockIdx.x) {
+        if (!p.b_resident || tile == first_tile) {
           for (int t = 0; t < ntaps; ++t) {
             mbar_wait(&b_empty[b_slot], b_phase ^ 1);
             mbar_expect_tx_if(leader, &b_full[b_slot], b_tile_bytes);
             bulk_g2s_if(leader, b_ring_addr + b_slot * b_tile_bytes, wtile, b_tile_bytes, &b_full[b_slot]);
-            wtile += b_tile_bytes / 2;
+            wtile += (PAIR ? 2 : 1) * (b_tile_bytes / 2);
             if (++b_slot == p.n_b_slots) { b_slot = 0; b_phase ^= 1; }
           }
         }
+      }
+    }
+  } else if (warp == 1 && PAIR && rank != 0) {
+    // ===================== relay (non-leader CTA of a pair): forward every completed full-barrier phase of this
+    // CTA to the leader's barrier of the same slot, in the order the leader's MMA loop waits for them =====================
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t a_full_remote = mapa_u32(smem_u32(a_full), 0);
+    const uint32_t b_full_remote = mapa_u32(smem_u32(b_full), 0);
+    int a_slot = 0, b_slot = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    uint32_t it = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
+      for (int g = 0; g < p.n_groups; ++g) {
+        mbar_wait(&a_full[a_slot], a_phase);
+        mbar_arrive_remote_if(leader, a_full_remote + a_slot * 8);
+        const int ntaps = p.group_ntaps[g];
+        for (int t = 0; t < ntaps; ++t) {
+          if (!p.b_resident || it == 0) {
+            mbar_wait(&b_full[b_slot], b_phase);
+            mbar_arrive_remote_if(leader, b_full_remote + b_slot * 8);
+          }
+          if (++b_slot == p.n_b_slots) { b_slot = 0; b_phase ^= (p.b_resident ? 0u : 1u); }
+        }
+        if (++a_slot == p.n_a_slots) { a_slot = 0; a_phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -180,41 +226,52 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
     const uint32_t a_lo0 = ((a_plane_bytes >> 4) << 16) + (smem_u32(a_ring) >> 4) + (uint32_t)p.halo_before;
-    const uint32_t b_lo0 = (((uint32_t)N_TILE * 16u >> 4) << 16) + (smem_u32(b_ring) >> 4);
+    const uint32_t b_lo0 = (((uint32_t)NB_ROWS * 16u >> 4) << 16) + (smem_u32(b_ring) >> 4);
     const uint32_t a_kstep = 2u * (a_plane_bytes >> 4);                      // two planes per K=16 MMA
-    constexpr uint32_t b_kstep = 2u * N_TILE;
+    constexpr uint32_t b_kstep = 2u * NB_ROWS;
     const uint32_t a_slot_units = a_slot_bytes >> 4;
     constexpr uint32_t b_tile_units = b_tile_bytes >> 4;
     int a_slot = 0, b_slot = 0;
     uint32_t a_phase = 0, b_phase = 0;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
       const uint32_t stage = it & 1;
-      mbar_wait(&acc_empty[stage], ((it >> 1) & 1) ^ 1);
+      if (PAIR) mbar_wait_cluster(&acc_empty[stage], ((it >> 1) & 1) ^ 1);
+      else mbar_wait(&acc_empty[stage], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + stage * ACC_COLS;
       uint32_t accumulate = 0;
       for (int g = 0; g < p.n_groups; ++g) {
-        mbar_wait(&a_full[a_slot], a_phase);
+        if (PAIR) mbar_wait_cluster(&a_full[a_slot], a_phase);
+        else mbar_wait(&a_full[a_slot], a_phase);
         const uint32_t a_grp = a_lo0 + a_slot * a_slot_units;
         const int tofs = p.group_tapofs[g];
         const int ntaps = p.group_ntaps[g];
         for (int t = 0; t < ntaps; ++t) {
-          if (!p.b_resident || it == 0) mbar_wait(&b_full[b_slot], b_phase);
+          if (!p.b_resident || it == 0) {
+            if (PAIR) mbar_wait_cluster(&b_full[b_slot], b_phase);
+            else mbar_wait(&b_full[b_slot], b_phase);
+          }
           tc_fence_after();
           const uint32_t a_tap = a_grp + (uint32_t)p.tap_shift[tofs + t];    // shift in pixels == 16-byte units
           const uint32_t b_tap = b_lo0 + b_slot * b_tile_units;
 #pragma unroll
           for (int k = 0; k < KP; ++k) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              umma_bf16_if(leader, acc + mt * N_TILE, a_tap + k * a_kstep + mt * 128u, desc_hi, b_tap + k * b_kstep, desc_hi,
-                           IDESC, (k == 0) ? accumulate : 1u);
+            for (int mt = 0; mt < MT; ++mt) {
+              if (PAIR)
+                umma2_bf16_if(leader, acc + mt * N_TILE, a_tap + k * a_kstep + mt * 128u, desc_hi, b_tap + k * b_kstep, desc_hi,
+                              IDESC, (k == 0) ? accumulate : 1u);
+              else
+                umma_bf16_if(leader, acc + mt * N_TILE, a_tap + k * a_kstep + mt * 128u, desc_hi, b_tap + k * b_kstep, desc_hi,
+                             IDESC, (k == 0) ? accumulate : 1u);
+            }
           }
-          if (!p.b_resident) tc_commit_if(leader, &b_empty[b_slot]);   // frees the weight slot once these MMAs retire
+          // commits free the weight slot / halo slot (in both CTAs of a pair) once these MMAs retire
+          if (!p.b_resident) { if (PAIR) tc_commit2_if(leader, &b_empty[b_slot]); else tc_commit_if(leader, &b_empty[b_slot]); }
           if (t == ntaps - 1) {
-            tc_commit_if(leader, &a_empty[a_slot]);
-            if (g == p.n_groups - 1) tc_commit_if(leader, &acc_full[stage]);
+            if (PAIR) tc_commit2_if(leader, &a_empty[a_slot]); else tc_commit_if(leader, &a_empty[a_slot]);
+            if (g == p.n_groups - 1) { if (PAIR) tc_commit2_if(leader, &acc_full[stage]); else tc_commit_if(leader, &acc_full[stage]); }
           }
           accumulate = 1;
           if (++b_slot == p.n_b_slots) { b_slot = 0; b_phase ^= (p.b_resident ? 0u : 1u); }
@@ -232,11 +289,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     constexpr int NSUB = POOL ? kEpiWarps / 8 : kEpiWarps / 4;
     const int img = p.Hp * p.Wp;
     uint32_t it = POOL ? group : 0;
-    const int tile_step = POOL ? 2 * gridDim.x : gridDim.x;
-    for (int tile = blockIdx.x + (POOL ? group * gridDim.x : 0); tile < total_tiles; tile += tile_step, it += (POOL ? 2 : 1)) {
+    const int tile_step = POOL ? 2 * tile_stride : tile_stride;
+    const uint32_t acc_empty_remote = PAIR ? mapa_u32(smem_u32(acc_empty), 0) : 0u;   // the leader's acc_empty barriers
+    for (int tile = first_tile + (POOL ? group * tile_stride : 0); tile < total_tiles; tile += tile_step, it += (POOL ? 2 : 1)) {
       const uint32_t stage = it & 1;
       const int n_tile = tile % p.n_n_tiles;
-      const int tile_start = conv_tile_start<POOL>(p, tile / p.n_n_tiles, TM);
+      const int tile_start = conv_tile_start<POOL>(p, tile / p.n_n_tiles, TILE_POS) + rank_ofs;
       const int cout_base = n_tile * N_TILE;
       uint8_t* stage_buf = pool_stage + (it & 1) * stage_bytes;
       const uint32_t acc = tmem_base + stage * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
@@ -270,7 +328,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           // this warp's last TMEM read of the stage: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[stage]);
+          if (PAIR) mbar_arrive_remote_if(lane == 0 ? 1u : 0u, acc_empty_remote + stage * 8);
+          else if (lane == 0) mbar_arrive(&acc_empty[stage]);
         }
         if (POOL) {
           // stage relu(acc + bias) as bf16 (zeros at padded positions: the pool's padding) for the pooling pass
@@ -373,15 +432,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         // a warp with no chunk in this configuration still takes part in the accumulator hand-back
         mbar_wait(&acc_full[stage], (it >> 1) & 1);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[stage]);
+        if (PAIR) mbar_arrive_remote_if(lane == 0 ? 1u : 0u, acc_empty_remote + stage * 8);
+        else if (lane == 0) mbar_arrive(&acc_empty[stage]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();            // the peer may still read this CTA's smem / signal its barriers until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

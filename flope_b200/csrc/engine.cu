@@ -69,6 +69,7 @@ struct ConvLayer {
   int relu;
   int out_mode;
   bool pool = false;             // stem only: fused 3x3/s2 max-pool epilogue
+  bool pair = false;             // CTA-pair kernel (cluster of 2, tcgen05 cta_group::2, M = 256)
   // projection shortcut folded into this conv as extra K groups (block 0 of layers 2-4):
   int short_buf = -1, cin2 = 0;
   std::string wkey2, bnkey2;
@@ -83,28 +84,46 @@ struct ConvLayer {
   float* d_bias = nullptr;
 };
 
-template <int N_TILE, int MT, int KP, bool POOL>
+template <int N_TILE, int MT, int KP, bool POOL, bool PAIR>
 cudaError_t conv_set_attr() {
-  return cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, MT, KP, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  if (e == cudaSuccess && PAIR)
+    e = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+  return e;
 }
-template <int N_TILE, int MT, int KP, bool POOL>
-void conv_launch_t(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  conv_igemm_kernel<N_TILE, MT, KP, POOL><<<grid, kConvThreads, smem, st>>>(p);
+template <int N_TILE, int MT, int KP, bool POOL, bool PAIR>
+cudaError_t conv_launch_t(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;      // PAIR: the two CTAs of a cluster share a TPC
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR>, p);
 }
 
-// (N_TILE, MT, KP, POOL): output channels per tile, 128-pixel sub-tiles per tile, K=16 MMAs per weight tile,
-// fused 3x3/s2 max-pool epilogue (stem)
-#define FOR_EACH_CONV_CFG(X) X(64, 4, 4, false) X(64, 4, 1, false) X(128, 2, 4, false) X(64, 3, 1, true)
+// (N_TILE, MT, KP, POOL, PAIR): output channels per tile, 128-pixel sub-tiles per CTA and tile, K=16 MMAs per weight
+// tile, fused 3x3/s2 max-pool epilogue (stem), CTA-pair (cta_group::2) kernel
+#define FOR_EACH_CONV_CFG(X)                                                                       \
+  X(64, 4, 4, false, false) X(64, 4, 1, false, false) X(128, 2, 4, false, false) X(64, 3, 1, true, false) \
+  X(64, 4, 4, false, true) X(64, 4, 1, false, true) X(128, 2, 4, false, true) X(256, 1, 4, false, true)
 
 cudaError_t conv_set_all_attrs() {
   cudaError_t e;
-#define X(N, M, K, P) if ((e = conv_set_attr<N, M, K, P>()) != cudaSuccess) return e;
+#define X(N, M, K, P, R) if ((e = conv_set_attr<N, M, K, P, R>()) != cudaSuccess) return e;
   FOR_EACH_CONV_CFG(X)
 #undef X
   return cudaSuccess;
 }
-bool conv_launch(int n_tile, int mt, const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-#define X(N, M, K, P) if (n_tile == N && mt == M && p.kc8 == 2 * K && (p.pool_rows > 0) == P) { conv_launch_t<N, M, K, P>(p, grid, smem, st); return true; }
+// returns false when no kernel instance matches; *err receives the launch status otherwise
+bool conv_launch(int n_tile, int mt, bool pair, const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st, cudaError_t* err) {
+#define X(N, M, K, P, R) if (n_tile == N && mt == M && p.kc8 == 2 * K && (p.pool_rows > 0) == P && pair == R) { *err = conv_launch_t<N, M, K, P, R>(p, grid, smem, st); return true; }
   FOR_EACH_CONV_CFG(X)
 #undef X
   return false;
@@ -120,6 +139,7 @@ struct flope_engine {
   std::map<std::string, int> act_names;          // debug name -> buffer index
   std::vector<ConvLayer> layers;
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
+  bool use_pair = true;                          // CTA-pair (cta_group::2) conv kernels; flope_debug_set "pair" 0 selects the single-CTA ones
   bool fuse_pool = false;                        // opt-in (flope_debug_set "fuse_pool"): measured no faster than stem + maxpool kernels
   bool can_fuse_pool = false;
   int buf_x0 = -1, buf_stem = -1, buf_pool_in = -1, buf_pool = -1, buf_mp_out = -1;
@@ -299,8 +319,11 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
   }
 
   // ---- tile configuration: persistent kernel, one CTA per SM, accumulator double-buffered in TMEM ----
+  L.pair = e->use_pair && !L.pool && L.kind != K_FC;   // fc: M = batch rows only, a handful of tiles - stays single-CTA
   L.n_tile = L.cout >= 128 ? 128 : 64;
+  if (L.pair && L.cout >= 256) L.n_tile = 256; // M = 256 x N = 256 MMAs: 8 KB of operand reads per SM per 128 tensor cycles
   L.mt = 256 / L.n_tile;                       // 2 stages x 256 columns = all 512 TMEM columns
+  const int nb_rows = L.pair ? L.n_tile / 2 : L.n_tile;   // weight rows per CTA and tile
   size_t pool_smem = 0;
   if (L.pool) {
     L.mt = 3;                                  // three conv rows of Wp positions per tile
@@ -312,7 +335,7 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
   const int halo = p.halo_before + p.halo_after;
   auto smem_of = [&](int n_a, int n_b) {
     return (size_t)1024 + (size_t)L.cout * sizeof(float) + (size_t)n_a * p.kc8 * (L.mt * 128 + halo) * 16 +
-           (size_t)n_b * p.kc8 * L.n_tile * 16 + pool_smem;
+           (size_t)n_b * p.kc8 * nb_rows * 16 + pool_smem;
   };
   // weight tiles are consumed every MT*kc8/2 MMAs, so several must be in flight to cover L2 latency;
   // halo tiles are consumed once per group: two or three slots are enough.  Rings run across tiles.
@@ -393,6 +416,13 @@ void pack_weights_host(const ConvLayer& L, const float* w, const std::vector<flo
   const int NT = L.n_tile;
   const int n_tiles = L.cout / NT;
   const size_t tile_elems = (size_t)p.kc8 * NT * 8;
+  // element index inside one packed weight tile: [k8][NT][8], or for the pair kernel [rank][k8][NT/2][8]
+  // (each CTA of a pair copies its half of the rows with one bulk copy)
+  const int half = NT / 2;
+  auto at = [&](int k8, int n, int j) -> size_t {
+    if (!L.pair) return ((size_t)k8 * NT + n) * 8 + j;
+    return (((size_t)(n / half) * p.kc8 + k8) * half + (n % half)) * 8 + j;
+  };
   out.assign((size_t)n_tiles * p.taps_total * tile_elems, __float2bfloat16_rn(0.f));
   for (int nt = 0; nt < n_tiles; ++nt) {
     size_t tile = (size_t)nt * p.taps_total;
@@ -407,7 +437,7 @@ void pack_weights_host(const ConvLayer& L, const float* w, const std::vector<flo
               float v = 0.f;
               if (g >= p.first_group2) {          // projection shortcut: (Cout, Cin2) 1x1 weights, their own BN scale
                 const int ci = L.group_cin[g] + k8 * 8 + j;
-                dst[((size_t)k8 * NT + n) * 8 + j] = __float2bfloat16_rn(w2[(size_t)co * L.cin2 + ci] * scale2[co]);
+                dst[at(k8, n, j)] = __float2bfloat16_rn(w2[(size_t)co * L.cin2 + ci] * scale2[co]);
                 continue;
               }
               switch (L.kind) {
@@ -431,7 +461,7 @@ void pack_weights_host(const ConvLayer& L, const float* w, const std::vector<flo
                   break;
                 }
               }
-              dst[((size_t)k8 * NT + n) * 8 + j] = __float2bfloat16_rn(v * scale[co]);   // BN scale folded in before the bf16 rounding
+              dst[at(k8, n, j)] = __float2bfloat16_rn(v * scale[co]);   // BN scale folded in before the bf16 rounding
             }
       }
     }
@@ -455,11 +485,14 @@ int run_conv(flope_engine* e, ConvLayer& L, int n, cudaStream_t st) {
   ConvParams p = L.p;
   p.n_positions = n * p.Hp * p.Wp;
   p.wgt = L.d_w; p.bias = L.d_bias;
-  const int TM = L.mt * 128;
+  const int TM = L.mt * 128 * (L.pair ? 2 : 1);            // positions per (pair) tile
   p.n_m_tiles = L.pool ? n * p.pool_rows : (p.n_positions + TM - 1) / TM;
   p.n_n_tiles = L.cout / L.n_tile;
-  dim3 grid((unsigned)std::min(p.n_m_tiles * p.n_n_tiles, e->num_sms));
-  if (!conv_launch(L.n_tile, L.mt, p, grid, L.smem, st)) return fail(FLOPE_EINVAL, "no kernel instance for " + L.name);
+  const int tiles = p.n_m_tiles * p.n_n_tiles;
+  dim3 grid((unsigned)(L.pair ? 2 * std::min(tiles, e->num_sms / 2) : std::min(tiles, e->num_sms)));
+  cudaError_t ce = cudaSuccess;
+  if (!conv_launch(L.n_tile, L.mt, L.pair, p, grid, L.smem, st, &ce)) return fail(FLOPE_EINVAL, "no kernel instance for " + L.name);
+  if (ce != cudaSuccess) return fail(FLOPE_ECUDA, "launch of " + L.name + ": " + cudaGetErrorString(ce));
   ++e->launches;
   return FLOPE_OK;
 }
@@ -875,6 +908,13 @@ int flope_debug_normalise_lut(float* d_out, void* stream) {
 int flope_debug_set(flope_engine* e, const char* key, int value) {
   if (!e || !key) return fail(FLOPE_EINVAL, "NULL argument");
   if (!std::strcmp(key, "use_graph")) { e->use_graph = value != 0; return FLOPE_OK; }
+  if (!std::strcmp(key, "pair")) {             // re-plans every layer; the packed weights depend on it, so they must be reloaded
+    e->use_pair = value != 0;
+    drop_graphs(e);
+    e->weights_loaded = false;
+    for (ConvLayer& L : e->layers) { int rc = plan_conv(e, L); if (rc) return rc; }
+    return FLOPE_OK;
+  }
   if (!std::strcmp(key, "fuse_pool")) {
     if (value && !e->can_fuse_pool) return fail(FLOPE_EINVAL, "fused stem pooling supports crop sides up to 252");
     e->fuse_pool = value != 0;

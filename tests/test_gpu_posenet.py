@@ -73,6 +73,32 @@ def test_fused_and_unfused_stem_agree_bitwise(eng224):
     assert torch.equal(a, b)
 
 
+def test_pair_and_single_cta_kernels_agree_bitwise(cuda_lib, net):
+    """The CTA-pair kernels (cluster of 2, tcgen05 cta_group::2, M = 256) and the single-CTA kernels accumulate
+    in the same K order, so every activation and the 9-vectors must be bit-identical; 300 crops of 224x224 make
+    several waves of pair tiles with a ragged last tile in every layer."""
+    x = synth.mixed_crops(75, 224).cuda()
+    x = torch.cat([x, x.flip(0), x.roll(7, 0), x.flip(3)], 0)
+    e = cuda_lib.Engine(0, max_batch=300, crop_hw=224)
+    try:
+        outs = {}
+        for pair in (1, 0):
+            e.debug_set("pair", pair)
+            e.load_state_dict(net.state_dict())
+            r9 = e.posenet_forward(x).clone()
+            acts = {}
+            for name in ("maxpool", "layer1.1", "layer2.0", "layer3.1", "layer4.1"):
+                buf, _ = e.debug_activation(name, x.shape[0])
+                acts[name] = buf.clone()
+            torch.cuda.synchronize()
+            outs[pair] = (r9, acts)
+        for name in outs[0][1]:
+            assert torch.equal(outs[0][1][name], outs[1][1][name]), name
+        assert torch.equal(outs[0][0], outs[1][0])
+    finally:
+        e.close()
+
+
 def test_orientation_within_half_degree_mean(eng224, net):
     x = synth.mixed_crops(32, 224)
     want = orot.procrustes_to_rotmat(onet.forward_fp32(net, x)).numpy()
