@@ -68,6 +68,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
+// start (prologue, barrier/TMEM set-up) while its predecessor drains; griddep_wait() blocks until the
+// predecessor grid has completed and its memory is visible, and must precede every access to activations.
+// Without the launch attribute both are no-ops.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
 // TMA bulk copy global -> shared (UBLKCP), completion on an mbarrier
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {

@@ -157,6 +157,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   if (PAIR) cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // everything above touched only static data (bias) and on-chip state; the activations of the previous layer
+  // are complete and visible after this point, and the next kernel may begin its own prologue
+  griddep_wait();
+  griddep_launch();
 
   if (warp == 0) {
     // ===================== TMA producer: whole warp runs the loop, one lane issues =====================

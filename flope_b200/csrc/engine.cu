@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/flope_b200.h"
@@ -91,21 +92,36 @@ cudaError_t conv_set_attr() {
     e = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
   return e;
 }
-template <int N_TILE, int MT, int KP, bool POOL, bool PAIR>
-cudaError_t conv_launch_t(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+// Launch with optional cluster size and programmatic dependent launch (the kernel may begin while its stream
+// predecessor drains; every kernel here calls griddep_wait() before touching activations).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, bool pdl,
+                     Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(kConvThreads);
+  cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;      // PAIR: the two CTAs of a cluster share a TPC
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;   // the two CTAs of a pair share a TPC
+    attr[na].val.clusterDim.x = cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR>, p);
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+template <int N_TILE, int MT, int KP, bool POOL, bool PAIR>
+cudaError_t conv_launch_t(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st, bool pdl) {
+  return launch_k(conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR>, grid, dim3(kConvThreads), smem, st, PAIR ? 2 : 1, pdl, p);
 }
 
 // (N_TILE, MT, KP, POOL, PAIR): output channels per tile, 128-pixel sub-tiles per CTA and tile, K=16 MMAs per weight
@@ -122,8 +138,8 @@ cudaError_t conv_set_all_attrs() {
   return cudaSuccess;
 }
 // returns false when no kernel instance matches; *err receives the launch status otherwise
-bool conv_launch(int n_tile, int mt, bool pair, const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st, cudaError_t* err) {
-#define X(N, M, K, P, R) if (n_tile == N && mt == M && p.kc8 == 2 * K && (p.pool_rows > 0) == P && pair == R) { *err = conv_launch_t<N, M, K, P, R>(p, grid, smem, st); return true; }
+bool conv_launch(int n_tile, int mt, bool pair, const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st, bool pdl, cudaError_t* err) {
+#define X(N, M, K, P, R) if (n_tile == N && mt == M && p.kc8 == 2 * K && (p.pool_rows > 0) == P && pair == R) { *err = conv_launch_t<N, M, K, P, R>(p, grid, smem, st, pdl); return true; }
   FOR_EACH_CONV_CFG(X)
 #undef X
   return false;
@@ -139,6 +155,7 @@ struct flope_engine {
   std::map<std::string, int> act_names;          // debug name -> buffer index
   std::vector<ConvLayer> layers;
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
+  bool use_pdl = true;                           // programmatic dependent launch between the backbone kernels
   bool use_pair = true;                          // CTA-pair (cta_group::2) conv kernels; flope_debug_set "pair" 0 selects the single-CTA ones
   bool fuse_pool = false;                        // opt-in (flope_debug_set "fuse_pool"): measured no faster than stem + maxpool kernels
   bool can_fuse_pool = false;
@@ -491,7 +508,7 @@ int run_conv(flope_engine* e, ConvLayer& L, int n, cudaStream_t st) {
   const int tiles = p.n_m_tiles * p.n_n_tiles;
   dim3 grid((unsigned)(L.pair ? 2 * std::min(tiles, e->num_sms / 2) : std::min(tiles, e->num_sms)));
   cudaError_t ce = cudaSuccess;
-  if (!conv_launch(L.n_tile, L.mt, L.pair, p, grid, L.smem, st, &ce)) return fail(FLOPE_EINVAL, "no kernel instance for " + L.name);
+  if (!conv_launch(L.n_tile, L.mt, L.pair, p, grid, L.smem, st, e->use_pdl, &ce)) return fail(FLOPE_EINVAL, "no kernel instance for " + L.name);
   if (ce != cudaSuccess) return fail(FLOPE_ECUDA, "launch of " + L.name + ": " + cudaGetErrorString(ce));
   ++e->launches;
   return FLOPE_OK;
@@ -515,7 +532,7 @@ int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
     const ActBuf& b = e->bufs[e->buf_mp_out];
     const long long total = (long long)(a.g.C / 8) * n * b.g.H * b.g.W;
     ProfScope ps(e, "maxpool", st);
-    maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(a.d, a.g, b.d, b.g, n);
+    launch_k(maxpool3x3s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, 1, e->use_pdl, a.d, a.g, b.d, b.g, n);
     ++e->launches;
   }
   for (; li + 1 < e->layers.size(); ++li)
@@ -525,7 +542,7 @@ int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
     const ActBuf& b = e->bufs[e->buf_pool];
     const int total_warps = (a.g.C / 8) * n;
     ProfScope ps(e, "avgpool", st);
-    avgpool_kernel<<<(total_warps + 7) / 8, 256, 0, st>>>(a.d, a.g, b.d, b.g, n);
+    launch_k(avgpool_kernel, dim3((total_warps + 7) / 8), dim3(256), 0, st, 1, e->use_pdl, a.d, a.g, b.d, b.g, n);
     ++e->launches;
   }
   if ((rc = run_conv(e, e->layers[li], n, st))) return rc;         // fc
@@ -572,8 +589,8 @@ int run_backbone(flope_engine* e, int n, cudaStream_t st) {
 int run_head(flope_engine* e, const float* feat, const float* r9_in, const float* R_in, int n, float* r9_out,
              float* R_out, double* Ryaw_out, cudaStream_t st) {
   ProfScope ps(e, "pose_head", st);
-  pose_head_kernel<<<n, kHeadThreads, 0, st>>>(
-      feat, e->feat_dim, e->d_wrot, e->d_brot, r9_in, n, r9_out, R_out, Ryaw_out, R_in);
+  launch_k(pose_head_kernel, dim3(n), dim3(kHeadThreads), 0, st, 1, e->use_pdl && feat != nullptr,
+           feat, e->feat_dim, (const float*)e->d_wrot, (const float*)e->d_brot, r9_in, n, r9_out, R_out, Ryaw_out, R_in);
   ++e->launches;
   CUDA_TRY(cudaGetLastError());
   return FLOPE_OK;
@@ -908,6 +925,7 @@ int flope_debug_normalise_lut(float* d_out, void* stream) {
 int flope_debug_set(flope_engine* e, const char* key, int value) {
   if (!e || !key) return fail(FLOPE_EINVAL, "NULL argument");
   if (!std::strcmp(key, "use_graph")) { e->use_graph = value != 0; return FLOPE_OK; }
+  if (!std::strcmp(key, "pdl")) { e->use_pdl = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "pair")) {             // re-plans every layer; the packed weights depend on it, so they must be reloaded
     e->use_pair = value != 0;
     drop_graphs(e);

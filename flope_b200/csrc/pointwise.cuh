@@ -14,6 +14,8 @@ __global__ void ingest_nchw_f32_kernel(const float* __restrict__ x, int n, int S
                                        Geom g) {
   // one thread = 4 consecutive pixels of one row: three 16-byte loads (one per channel plane),
   // one 32-byte run of two s2d pixels out
+  griddep_wait();
+  griddep_launch();
   const int S4 = S >> 2;
   const long long total = (long long)n * S * S4;
   const long long plane_sz = (long long)S * S;
@@ -46,6 +48,8 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 // Inputs are post-ReLU (>= 0) and padded positions hold zeros, so zero padding == -inf padding.
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, Geom gi, __nv_bfloat16* __restrict__ out,
                                     Geom go, int n) {
+  griddep_wait();
+  griddep_launch();
   const int C8 = gi.C >> 3;
   const long long total = (long long)C8 * n * go.H * go.W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -77,6 +81,8 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, Geom g
 // fc GEMM reads (plane c8, position = crop index).
 __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ in, Geom gi, __nv_bfloat16* __restrict__ out,
                                Geom go, int n) {
+  griddep_wait();
+  griddep_launch();
   const int C8 = gi.C >> 3;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;

@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(kHeadThreads) pose_head_kernel(const float* __
                                                                  double* __restrict__ Ryaw_out,
                                                                  const float* __restrict__ R_in) {
   __shared__ float s_part[kHeadThreads / 32][9];
+  griddep_wait();
+  griddep_launch();
   const int crop = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (feat) {
