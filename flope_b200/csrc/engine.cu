@@ -44,7 +44,7 @@ long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 Geom make_geom(int C, int H, int W, int pad, int max_batch) {
   Geom g;
   g.C = C; g.H = H; g.W = W; g.Hp = H + pad; g.Wp = W + pad;
-  g.base = (int)round_up(4 * g.Wp + 8, 8);
+  g.base = (int)round_up(8 * g.Wp + 8, 8);     // zero guard: the pooled stem's carry tile reaches 6 rows above a crop
   const long long npos = (long long)max_batch * g.Hp * g.Wp;
   g.plane = g.base + round_up(npos, 1024) + kMaxTM + round_up(4 * g.Wp + 8, 8);
   return g;
@@ -85,12 +85,9 @@ struct ConvLayer {
   float* d_bias = nullptr;
 };
 
-template <int N_TILE, int MT, int KP, bool POOL, bool PAIR>
+template <int N_TILE, int MT, int KP, bool POOL, bool PAIR, int TAPS>
 cudaError_t conv_set_attr() {
-  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-  if (e == cudaSuccess && PAIR)
-    e = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
-  return e;
+  return cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
 }
 // Launch with optional cluster size and programmatic dependent launch (the kernel may begin while its stream
 // predecessor drains; every kernel here calls griddep_wait() before touching activations).
@@ -119,27 +116,36 @@ cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-template <int N_TILE, int MT, int KP, bool POOL, bool PAIR>
+template <int N_TILE, int MT, int KP, bool POOL, bool PAIR, int TAPS>
 cudaError_t conv_launch_t(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st, bool pdl) {
-  return launch_k(conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR>, grid, dim3(kConvThreads), smem, st, PAIR ? 2 : 1, pdl, p);
+  return launch_k(conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR, TAPS>, grid, dim3(kConvThreads), smem, st, PAIR ? 2 : 1, pdl, p);
 }
 
-// (N_TILE, MT, KP, POOL, PAIR): output channels per tile, 128-pixel sub-tiles per CTA and tile, K=16 MMAs per weight
-// tile, fused 3x3/s2 max-pool epilogue (stem), CTA-pair (cta_group::2) kernel
-#define FOR_EACH_CONV_CFG(X)                                                                       \
-  X(64, 4, 4, false, false) X(64, 4, 1, false, false) X(128, 2, 4, false, false) X(64, 3, 1, true, false) \
-  X(64, 4, 4, false, true) X(64, 4, 1, false, true) X(128, 2, 4, false, true) X(256, 1, 4, false, true)
+// (N_TILE, MT, KP, POOL, PAIR, TAPS): output channels per tile, 128-pixel sub-tiles per CTA and tile, K=16 MMAs per weight
+// tile, fused 3x3/s2 max-pool epilogue (stem), CTA-pair (cta_group::2) kernel, tap issue order (16 = stem rows, 0 = tables)
+#define FOR_EACH_CONV_CFG(X)                                                                                   \
+  /* single-CTA */                                                                                             \
+  X(64, 4, 4, false, false, 0) X(128, 2, 4, false, false, 0)                                                   \
+  X(64, 4, 1, false, false, 16) X(64, 4, 1, true, false, 16)                                                   \
+  /* CTA pair */                                                                                               \
+  X(64, 4, 4, false, true, 0) X(128, 2, 4, false, true, 0) X(256, 1, 4, false, true, 0)                        \
+  X(64, 4, 1, false, true, 16) X(64, 4, 1, true, true, 16)
 
 cudaError_t conv_set_all_attrs() {
   cudaError_t e;
-#define X(N, M, K, P, R) if ((e = conv_set_attr<N, M, K, P, R>()) != cudaSuccess) return e;
+#define X(N, M, K, P, R, T) if ((e = conv_set_attr<N, M, K, P, R, T>()) != cudaSuccess) return e;
   FOR_EACH_CONV_CFG(X)
 #undef X
   return cudaSuccess;
 }
 // returns false when no kernel instance matches; *err receives the launch status otherwise
-bool conv_launch(int n_tile, int mt, bool pair, const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st, bool pdl, cudaError_t* err) {
-#define X(N, M, K, P, R) if (n_tile == N && mt == M && p.kc8 == 2 * K && (p.pool_rows > 0) == P && pair == R) { *err = conv_launch_t<N, M, K, P, R>(p, grid, smem, st, pdl); return true; }
+bool conv_launch(int n_tile, int mt, bool pair, int taps, const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st, bool pdl,
+                 cudaError_t* err) {
+#define X(N, M, K, P, R, T)                                                                                        \
+  if (n_tile == N && mt == M && p.kc8 == 2 * K && (p.pool_rows > 0) == P && pair == R && taps == T) {              \
+    *err = conv_launch_t<N, M, K, P, R, T>(p, grid, smem, st, pdl);                                                \
+    return true;                                                                                                   \
+  }
   FOR_EACH_CONV_CFG(X)
 #undef X
   return false;
@@ -157,7 +163,7 @@ struct flope_engine {
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
   bool use_pdl = true;                           // programmatic dependent launch between the backbone kernels
   bool use_pair = true;                          // CTA-pair (cta_group::2) conv kernels; flope_debug_set "pair" 0 selects the single-CTA ones
-  bool fuse_pool = false;                        // opt-in (flope_debug_set "fuse_pool"): measured no faster than stem + maxpool kernels
+  bool fuse_pool = false;                        // stem conv + max-pool in one kernel (default whenever the crop side allows it)
   bool can_fuse_pool = false;
   int buf_x0 = -1, buf_stem = -1, buf_pool_in = -1, buf_pool = -1, buf_mp_out = -1;
   float* d_feat = nullptr;                       // (max_batch, 2048) fp32
@@ -336,22 +342,23 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
   }
 
   // ---- tile configuration: persistent kernel, one CTA per SM, accumulator double-buffered in TMEM ----
-  L.pair = e->use_pair && !L.pool && L.kind != K_FC;   // fc: M = batch rows only, a handful of tiles - stays single-CTA
+  L.pair = e->use_pair && L.kind != K_FC;   // fc: M = batch rows only, a handful of tiles - stays single-CTA
   L.n_tile = L.cout >= 128 ? 128 : 64;
   if (L.pair && L.cout >= 256) L.n_tile = 256; // M = 256 x N = 256 MMAs: 8 KB of operand reads per SM per 128 tensor cycles
   L.mt = 256 / L.n_tile;                       // 2 stages x 256 columns = all 512 TMEM columns
   const int nb_rows = L.pair ? L.n_tile / 2 : L.n_tile;   // weight rows per CTA and tile
   size_t pool_smem = 0;
+  int span = L.mt * 128;                       // positions of the halo tile one tile covers (without the halo)
   if (L.pool) {
-    L.mt = 3;                                  // three conv rows of Wp positions per tile
-    if (3 * p.Wp > L.mt * 128) return fail(FLOPE_EINVAL, "fused stem pooling needs 3*(S/2+2) <= 384 (crop side <= 252)");
-    p.pool_rows = p.H / 2;
-    p.pool_cols = p.W / 2;
-    pool_smem = (size_t)2 * (L.n_tile / 8) * (L.mt * 128) * 16;
+    // sub-tile = one conv row (lane = column), tile = four rows, work item = a quarter of a crop
+    if (p.Wp > 128 || p.H % (4 * kPoolSplit)) return fail(FLOPE_EINVAL, "fused stem pooling needs S/2+2 <= 128 and S % 32 == 0");
+    p.pool_rows = p.H / kPoolSplit;
+    span = 3 * p.Wp + 128;
+    pool_smem = kPoolXchBytes;
   }
   const int halo = p.halo_before + p.halo_after;
   auto smem_of = [&](int n_a, int n_b) {
-    return (size_t)1024 + (size_t)L.cout * sizeof(float) + (size_t)n_a * p.kc8 * (L.mt * 128 + halo) * 16 +
+    return (size_t)1024 + (size_t)L.cout * sizeof(float) + (size_t)n_a * p.kc8 * (span + halo) * 16 +
            (size_t)n_b * p.kc8 * nb_rows * 16 + pool_smem;
   };
   // weight tiles are consumed every MT*kc8/2 MMAs, so several must be in flight to cover L2 latency;
@@ -379,11 +386,12 @@ int build_network(flope_engine* e) {
   int cur = add_buf(e, 64, s4, s4, 1, false, "maxpool");
   e->buf_mp_out = cur;
   add_conv(e, "conv1", K_STEM, 16, 64, e->buf_x0, e->buf_stem, -1, 1, OUT_PLAIN, "base.conv1.weight", "base.bn1");
-  if (3 * (s2 + 2) <= 384) {                   // fused stem + max-pool (crop side <= 252); larger crops keep two kernels
+  if (s2 + 2 <= 128) {                         // fused stem + max-pool (crop side <= 252); larger crops keep two kernels
     ConvLayer L = e->layers.back();
     L.name = "conv1+maxpool"; L.out_buf = e->buf_mp_out; L.pool = true;
     e->stem_pool = L;
     e->can_fuse_pool = true;
+    e->fuse_pool = true;
   }
   int C = 64, side = s4;
   for (int stage = 1; stage <= 4; ++stage) {
@@ -503,12 +511,14 @@ int run_conv(flope_engine* e, ConvLayer& L, int n, cudaStream_t st) {
   p.n_positions = n * p.Hp * p.Wp;
   p.wgt = L.d_w; p.bias = L.d_bias;
   const int TM = L.mt * 128 * (L.pair ? 2 : 1);            // positions per (pair) tile
-  p.n_m_tiles = L.pool ? n * p.pool_rows : (p.n_positions + TM - 1) / TM;
   p.n_n_tiles = L.cout / L.n_tile;
-  const int tiles = p.n_m_tiles * p.n_n_tiles;
+  // work items: (pair) tiles, or for the pooled stem quarter-crops (two per pair)
+  p.n_work = L.pool ? n * kPoolSplit / (L.pair ? 2 : 1) : (p.n_positions + TM - 1) / TM * p.n_n_tiles;
+  const int tiles = p.n_work;
   dim3 grid((unsigned)(L.pair ? 2 * std::min(tiles, e->num_sms / 2) : std::min(tiles, e->num_sms)));
   cudaError_t ce = cudaSuccess;
-  if (!conv_launch(L.n_tile, L.mt, L.pair, p, grid, L.smem, st, e->use_pdl, &ce)) return fail(FLOPE_EINVAL, "no kernel instance for " + L.name);
+  const int taps = L.kind == K_STEM ? 16 : 0;   // the stem's 4x4 window is issued a row of taps at a time
+  if (!conv_launch(L.n_tile, L.mt, L.pair, taps, p, grid, L.smem, st, e->use_pdl, &ce)) return fail(FLOPE_EINVAL, "no kernel instance for " + L.name);
   if (ce != cudaSuccess) return fail(FLOPE_ECUDA, "launch of " + L.name + ": " + cudaGetErrorString(ce));
   ++e->launches;
   return FLOPE_OK;
@@ -931,6 +941,7 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
     drop_graphs(e);
     e->weights_loaded = false;
     for (ConvLayer& L : e->layers) { int rc = plan_conv(e, L); if (rc) return rc; }
+    if (e->can_fuse_pool) { int rc = plan_conv(e, e->stem_pool); if (rc) return rc; }
     return FLOPE_OK;
   }
   if (!std::strcmp(key, "fuse_pool")) {

@@ -40,8 +40,8 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("fuse_pool", [0, 1])
 def test_every_block_matches_oracle(eng224, net, fuse_pool):
-    """fuse_pool=0 is the default path (stem kernel + max-pool kernel); fuse_pool=1 is the opt-in single kernel
-    (stem conv + BN + ReLU + max-pool, no stem tensor in HBM), which must give the same tensors."""
+    """fuse_pool=1 is the default path for crops up to 252 px (stem conv + BN + ReLU + max-pool in one kernel, no
+    stem tensor in HBM); fuse_pool=0 is the two-kernel path larger crops use, which must give the same tensors."""
     x = synth.mixed_crops(6, 224)
     acts = onet.trunk_activations(net, x)
     eng224.debug_set("fuse_pool", fuse_pool)
@@ -55,7 +55,7 @@ def test_every_block_matches_oracle(eng224, net, fuse_pool):
             assert _rel(got, acts[name]) < 2e-2, name
         assert _rel(r9.cpu(), acts["r9"]) < 2e-2
     finally:
-        eng224.debug_set("fuse_pool", 0)
+        eng224.debug_set("fuse_pool", 1)
 
 
 def test_fused_and_unfused_stem_agree_bitwise(eng224):
@@ -68,7 +68,6 @@ def test_fused_and_unfused_stem_agree_bitwise(eng224):
     b = eng224.posenet_forward(x).clone()
     pb, _ = eng224.debug_activation("maxpool", 9)
     torch.cuda.synchronize()
-    eng224.debug_set("fuse_pool", 0)
     assert torch.equal(pa, pb)
     assert torch.equal(a, b)
 

@@ -6,6 +6,8 @@ from flope_b200 import _lib, synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 224
 eng = _lib.Engine(0, max_batch=B, crop_hw=S)
+for kv in filter(None, os.environ.get("FLOPE_SET", "").split(",")):
+    eng.debug_set(kv.split("=")[0], int(kv.split("=")[1]))
 eng.load_state_dict(synth.random_state_dict(0))
 x = torch.rand((B, 3, S, S), device="cuda")
 out = torch.empty((B, 9), device="cuda")

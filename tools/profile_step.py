@@ -15,6 +15,8 @@ ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--frames", type=int, default=0, help="also run the ROI kernel on this many 1080p frames x 32 boxes")
 a = ap.parse_args()
 eng = _lib.Engine(0, max_batch=a.batch, crop_hw=a.size)
+for kv in filter(None, os.environ.get("FLOPE_SET", "").split(",")):   # e.g. FLOPE_SET=fuse_pool=1,use_graph=0
+    eng.debug_set(kv.split("=")[0], int(kv.split("=")[1]))
 eng.load_state_dict(synth.random_state_dict(0))
 x = torch.rand((a.batch, 3, a.size, a.size), device="cuda")
 out = torch.empty((a.batch, 9), device="cuda")
