@@ -149,7 +149,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   // POOL: lane-31 hand-over between the four lane-quarter warps of a channel slice: [parity][slice][quarter][2 rows][8]
   uint32_t* pool_xch = reinterpret_cast<uint32_t*>(b_ring + (size_t)p.n_b_slots * b_tile_bytes);
 
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0 so that the compiler knows the warp index is warp-uniform: the role branches become
+  // uniform branches and the MMA / TMA issue code can live in the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader (issues the MMAs)
   const int first_work = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // work is dealt to pairs (or CTAs) round-robin
