@@ -187,6 +187,7 @@ class Engine:
         return int(lib().flope_engine_last_launches(self._h))
 
     def profile(self, enable=True):
+        """1/True: an event pair per launch; 2: one pair around the trunk's conv chain; 0/False: off."""
         check(lib().flope_engine_profile(self._h, int(enable)))
 
     def profile_read(self, max_entries=65536):

@@ -178,6 +178,7 @@ struct flope_engine {
   std::vector<GraphEntry> graphs;
   // optional per-launch CUDA-event timing (bench.py roofline pass)
   bool profile = false;
+  int profile_mode = 0;                          // 1: one event pair per launch; 2: one pair around the trunk's conv chain
   std::vector<std::string> prof_names;
   std::vector<cudaEvent_t> prof_ev;              // start/stop pairs, in launch order
 };
@@ -493,9 +494,10 @@ void pack_weights_host(const ConvLayer& L, const float* w, const std::vector<flo
   }
 }
 
-struct ProfScope {                               // records a start/stop event pair around one launch
+struct ProfScope {                               // records a start/stop event pair around one launch (mode 1) or a chain (mode 2)
   flope_engine* e; cudaStream_t st; bool on;
-  ProfScope(flope_engine* e_, const std::string& name, cudaStream_t st_) : e(e_), st(st_), on(e_->profile) {
+  ProfScope(flope_engine* e_, const std::string& name, cudaStream_t st_, int mode = 1)
+      : e(e_), st(st_), on(e_->profile && e_->profile_mode == mode) {
     if (!on) return;
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
@@ -533,11 +535,14 @@ int grid_for(long long total, int block) {
 int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
   int rc;
   size_t li = 0;
+  // mode 2: the stem .. layer4 conv_igemm launches as they run in production (back to back, programmatic
+  // dependent launch overlapping each prologue with its predecessor's tail) between ONE pair of events
+  ProfScope* chain = new ProfScope(e, "conv_chain", st, 2);
   if (e->fuse_pool) {
     ++li;
-    if ((rc = run_conv(e, e->stem_pool, n, st))) return rc;        // stem conv + BN + ReLU + max-pool in one kernel
+    if ((rc = run_conv(e, e->stem_pool, n, st))) { delete chain; return rc; }   // stem conv + BN + ReLU + max-pool in one kernel
   } else {
-    if ((rc = run_conv(e, e->layers[li++], n, st))) return rc;     // stem
+    if ((rc = run_conv(e, e->layers[li++], n, st))) { delete chain; return rc; }   // stem
     const ActBuf& a = e->bufs[e->buf_stem];
     const ActBuf& b = e->bufs[e->buf_mp_out];
     const long long total = (long long)(a.g.C / 8) * n * b.g.H * b.g.W;
@@ -546,7 +551,8 @@ int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
     ++e->launches;
   }
   for (; li + 1 < e->layers.size(); ++li)
-    if ((rc = run_conv(e, e->layers[li], n, st))) return rc;
+    if ((rc = run_conv(e, e->layers[li], n, st))) { delete chain; return rc; }
+  delete chain;
   {
     const ActBuf& a = e->bufs[e->buf_pool_in];
     const ActBuf& b = e->bufs[e->buf_pool];
@@ -891,6 +897,7 @@ int flope_engine_profile(flope_engine* e, int enable) {
   for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
   e->prof_ev.clear(); e->prof_names.clear();
   e->profile = enable != 0;
+  e->profile_mode = enable;
   return FLOPE_OK;
 }
 

@@ -101,8 +101,11 @@ int flope_infer_frames(flope_engine* e, const uint8_t* d_frames, int n_frames, i
 /* Number of kernels the last call on this engine launched (bench.py reports it). */
 int flope_engine_last_launches(const flope_engine* e);
 
-/* Per-launch CUDA-event timing for bench.py's roofline pass.  flope_engine_profile(e,1) clears and
- * enables recording (one start/stop event pair around every kernel launch of subsequent calls);
+/* CUDA-event timing for bench.py's roofline pass.  flope_engine_profile(e,1) clears and enables
+ * recording of one start/stop event pair around every kernel launch of subsequent calls (isolated
+ * launches: the events between kernels prevent programmatic-dependent-launch overlap);
+ * flope_engine_profile(e,2) records ONE pair around the trunk's conv_igemm chain (stem .. layer4, the
+ * launches back to back exactly as in production, entry name "conv_chain"); 0 disables.
  * flope_engine_profile_read synchronises the device and returns the number of recorded launches,
  * their names as a '\n'-joined string and their durations in milliseconds. */
 int flope_engine_profile(flope_engine* e, int enable);
