@@ -161,6 +161,7 @@ struct flope_engine {
   std::map<std::string, int> act_names;          // debug name -> buffer index
   std::vector<ConvLayer> layers;
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
+  int roi_strip = 14;                            // output rows per CTA of the bilinear ROI kernel (even; crops below 448 px)
   bool use_pdl = true;                           // programmatic dependent launch between the backbone kernels
   bool use_pair = true;                          // CTA-pair (cta_group::2) conv kernels; flope_debug_set "pair" 0 selects the single-CTA ones
   bool fuse_pool = false;                        // stem conv + max-pool in one kernel (default whenever the crop side allows it)
@@ -632,7 +633,7 @@ int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W
   if (interp != FLOPE_INTERP_LANCZOS4) {           // bilinear kernel: one thread per column pair
     const int cols = S / 2;
     block = cols >= 256 ? 256 : ((cols + 31) / 32 * 32);
-    rp.rows_per_strip = S >= 448 ? 128 : 56;
+    rp.rows_per_strip = S >= 448 ? 128 : e->roi_strip;
     grid = dim3((cols + block - 1) / block, (S + rp.rows_per_strip - 1) / rp.rows_per_strip, n);
   }
   ProfScope ps(e, "roi_crop", st);
@@ -942,6 +943,11 @@ int flope_debug_normalise_lut(float* d_out, void* stream) {
 int flope_debug_set(flope_engine* e, const char* key, int value) {
   if (!e || !key) return fail(FLOPE_EINVAL, "NULL argument");
   if (!std::strcmp(key, "use_graph")) { e->use_graph = value != 0; return FLOPE_OK; }
+  if (!std::strcmp(key, "roi_strip")) {
+    if (value < 2 || value > kRoiMaxStripRows || (value & 1)) return fail(FLOPE_EINVAL, "roi_strip must be even and in [2,128]");
+    e->roi_strip = value;
+    return FLOPE_OK;
+  }
   if (!std::strcmp(key, "pdl")) { e->use_pdl = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "pair")) {             // re-plans every layer; the packed weights depend on it, so they must be reloaded
     e->use_pair = value != 0;

@@ -155,28 +155,40 @@ __global__ void __launch_bounds__(256) roi_bilinear_kernel(const __grid_constant
   const uint32_t row_bytes = (uint32_t)p.W * 3u;
 
   uint32_t h0[2][NCH], h1[2][NCH];         // (horizontally filtered row) >> 4 for source rows u and u+1, per column
-  auto hrow = [&](int urow, uint32_t (&dst)[2][NCH]) {
+  // The tap bytes of a source row are loaded (load_raw) and filtered (filt) in two steps so that the loads of the
+  // row the NEXT output row needs are in flight while this output row is computed (software pipelining: the
+  // kernel is latency bound, not issue bound).
+  struct Raw { uint32_t a[2][NCH], b[2][NCH]; };
+  auto load_raw = [&](int urow, Raw& w) {
     const uint32_t r = (uint32_t)min(max(urow, 0), sh - 1);
     const uint8_t* row = img + r * row_bytes;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const uint8_t* pa = row + oa[k] * 3u;
       const uint8_t* pb = row + ob[k] * 3u;
-      dst[k][0] = (uint32_t)((int)__ldg(pa) * cx0[k] + (int)__ldg(pb) * cx1[k]) >> 4;
-      dst[k][1] = (uint32_t)((int)__ldg(pa + 1) * cx0[k] + (int)__ldg(pb + 1) * cx1[k]) >> 4;
-      dst[k][2] = (uint32_t)((int)__ldg(pa + 2) * cx0[k] + (int)__ldg(pb + 2) * cx1[k]) >> 4;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { w.a[k][c] = __ldg(pa + c); w.b[k][c] = __ldg(pb + c); }
     }
     if (HAS_MASK) {
       const uint8_t* mrow = msk + r * (uint32_t)p.W;
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
-        dst[k][3] = (uint32_t)((int)__ldg(mrow + oa[k]) * cx0[k] + (int)__ldg(mrow + ob[k]) * cx1[k]) >> 4;
+      for (int k = 0; k < 2; ++k) { w.a[k][NCH - 1] = __ldg(mrow + oa[k]); w.b[k][NCH - 1] = __ldg(mrow + ob[k]); }
     }
+  };
+  auto filt = [&](const Raw& w, uint32_t (&dst)[2][NCH]) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) dst[k][c] = (uint32_t)((int)w.a[k][c] * cx0[k] + (int)w.b[k][c] * cx1[k]) >> 4;
   };
 
   int u = s_sy[0];
-  hrow(u, h0);
-  hrow(u + 1, h1);
+  Raw nx;
+  load_raw(u, nx);
+  filt(nx, h0);
+  load_raw(u + 1, nx);
+  filt(nx, h1);
+  int nx_row = u - 1;                      // source row whose tap bytes `nx` holds unfiltered (none yet)
   const long long plane_sz = (long long)S * S;
   float* o32 = reinterpret_cast<float*>(p.out) + ((long long)crop * 3 * S + y_begin) * S + 2 * q;
   __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(p.out) +
@@ -191,12 +203,19 @@ __global__ void __launch_bounds__(256) roi_bilinear_kernel(const __grid_constant
         for (int k = 0; k < 2; ++k)
 #pragma unroll
           for (int c = 0; c < NCH; ++c) h0[k][c] = h1[k][c];
-        hrow(u_new + 1, h1);
+        if (nx_row != u_new + 1) load_raw(u_new + 1, nx);     // normally prefetched one output row ago
+        filt(nx, h1);
       } else {
-        hrow(u_new, h0);
-        hrow(u_new + 1, h1);
+        load_raw(u_new, nx);
+        filt(nx, h0);
+        load_raw(u_new + 1, nx);
+        filt(nx, h1);
       }
       u = u_new;
+    }
+    if (y + 1 < y_end && s_sy[y + 1 - y_begin] == u + 1) {    // the next output row slides the window by one source row
+      load_raw(u + 2, nx);
+      nx_row = u + 2;
     }
     const uint32_t b0 = s_b0[y - y_begin], b1 = s_b1[y - y_begin];
     float f[2][3];

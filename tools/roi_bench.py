@@ -31,7 +31,9 @@ def timeit(fn, reps=10):
 
 
 eng = _lib.Engine(0, max_batch=n, crop_hw=224)
-for mask_on in (True, False):
+for strip, mask_on in ((56, True), (56, False), (28, True), (28, False), (14, True), (112, True)):
+    eng.debug_set("roi_strip", strip)
+    print(f"{strip}-row strips", end=": ")
     m = mk if mask_on else None
     ms = timeit(lambda: eng.roi_crop(fr, m, bx, 224, _lib.INTERP_LINEAR, out_fmt=_lib.OUT_ENGINE))
     byts = float((3 * side ** 2 + (side ** 2 if mask_on else 0) + 301056 + 20).sum())
