@@ -20,7 +20,7 @@ SYMBOLS = [
     "flope_engine_load_weights", "flope_squarify_filter", "flope_roi_crop", "flope_posenet_forward",
     "flope_pose_head", "flope_nullify_yaw", "flope_infer_frames", "flope_engine_last_launches",
     "flope_debug_activation", "flope_debug_normalise_lut", "flope_debug_set",
-    "flope_engine_profile", "flope_engine_profile_read",
+    "flope_engine_profile", "flope_engine_profile_read", "flope_depth_values",
 ]
 
 
@@ -62,6 +62,9 @@ def lib():
         L.flope_debug_set.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.flope_engine_profile.argtypes = [C.c_void_p, C.c_int]
         L.flope_engine_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.c_int]
+        L.flope_depth_values.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]
         _lib = L
     return _lib
 
@@ -89,6 +92,33 @@ def _stream():
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def depth_values(depth, mask, boxes, near_plane, far_plane, depth_div=None, erode_k=10):
+    """flope_depth_values on device tensors: depth (H,W) float32 metres, or uint16 raw with depth_div;
+    mask (H,W) uint8; boxes (n,4) int32 xyxy  ->  (val (n,) float64 metres, count (n,) int32), both on the device."""
+    import torch
+    if not depth.is_cuda:
+        raise FlopeError("depth_values needs CUDA tensors (there is no CPU fallback)")
+    H, W = depth.shape
+    n = int(boxes.shape[0])
+    if depth.dtype == torch.uint16:
+        if depth_div is None:
+            raise FlopeError("uint16 depth needs depth_div (sensor units per metre)")
+        dtype, div = 1, float(depth_div)
+    elif depth.dtype == torch.float32:
+        dtype, div = 0, 1.0
+    else:
+        raise FlopeError(f"depth must be float32 or uint16, not {depth.dtype}")
+    dev = depth.device
+    scratch = torch.empty((H, W), dtype=torch.uint8, device=dev)
+    val = torch.empty((n,), dtype=torch.float64, device=dev)
+    cnt = torch.empty((n,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().flope_depth_values(dev.index or 0, _ptr(depth.contiguous()), dtype, div, _ptr(mask.contiguous()), H, W,
+                                       _ptr(boxes.contiguous()), n, float(near_plane), float(far_plane), int(erode_k),
+                                       _ptr(scratch), _ptr(val), _ptr(cnt), _stream()))
+    return val, cnt, scratch
 
 
 class Engine:

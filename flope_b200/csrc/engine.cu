@@ -17,6 +17,7 @@
 
 #include "../../include/flope_b200.h"
 #include "conv_igemm.cuh"
+#include "depth.cuh"
 #include "pointwise.cuh"
 #include "pose_head.cuh"
 #include "roi_crop.cuh"
@@ -888,6 +889,42 @@ int flope_infer_frames(flope_engine* e, const uint8_t* d_frames, int n_frames, i
                        d_R ? d_R + (size_t)done * 9 : nullptr, d_R_yaw ? d_R_yaw + (size_t)done * 9 : nullptr, st)))
       return rc;
   }
+  return FLOPE_OK;
+}
+
+int flope_depth_values(int device, const void* d_depth, int depth_dtype, float depth_div, const uint8_t* d_mask, int H, int W,
+                       const int32_t* d_boxes, int n, float near_plane, float far_plane, int erode_k, uint8_t* d_scratch,
+                       double* d_val, int32_t* d_count, void* stream) {
+  if (!d_depth || !d_mask || !d_scratch) return fail(FLOPE_EINVAL, "NULL argument");
+  if (n < 0 || (n > 0 && (!d_boxes || !d_val || !d_count))) return fail(FLOPE_EINVAL, "NULL argument");
+  if (H < 1 || W < 1 || erode_k < 1 || erode_k > kErodeMaxK) return fail(FLOPE_EINVAL, "bad frame size or erosion size (1..31)");
+  if (depth_dtype != 0 && depth_dtype != 1) return fail(FLOPE_EINVAL, "depth_dtype must be 0 (float32 metres) or 1 (uint16 raw)");
+  if (depth_dtype == 1 && !(depth_div > 0.f)) return fail(FLOPE_EINVAL, "depth_div must be positive");
+  CUDA_TRY(cudaSetDevice(device));
+  DepthParams dp{};
+  dp.depth = d_depth; dp.dtype = depth_dtype; dp.div = depth_div; dp.mask = d_mask; dp.H = H; dp.W = W;
+  dp.near_plane = near_plane; dp.far_plane = far_plane; dp.k = erode_k; dp.eroded = d_scratch;
+  {
+    // cv2.getStructuringElement(MORPH_ELLIPSE, (k,k)): row i is ones on [c - dx, c + dx + 1) with
+    // dx = round_half_even(c * sqrt((r*r - dy*dy) / (r*r))), dy = i - r, r = c = k/2 (checked against cv2 in the tests)
+    const int r = erode_k / 2, c = erode_k / 2;
+    const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    for (int i = 0; i < erode_k; ++i) {
+      const int dy = i - r;
+      int j1 = 0, j2 = 0;
+      if (std::abs(dy) <= r) {
+        const int dx = (int)std::nearbyint(c * std::sqrt((r * r - dy * dy) * inv_r2));
+        j1 = std::max(c - dx, 0);
+        j2 = std::min(c + dx + 1, erode_k);
+      }
+      dp.j1[i] = j1; dp.j2[i] = j2;
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((W + kErodeTileW - 1) / kErodeTileW, (H + kErodeTileH - 1) / kErodeTileH);
+  erode_valid_kernel<<<grid, 256, 0, st>>>(dp);
+  if (n > 0) box_depth_kernel<<<n, 256, 0, st>>>(dp, d_boxes, n, d_val, d_count);
+  CUDA_TRY(cudaGetLastError());
   return FLOPE_OK;
 }
 

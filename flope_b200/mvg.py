@@ -5,6 +5,7 @@ Same names, argument meaning and return types as the reference:
   bb_in_frame            sunflower/utils/mvg.py:345-351
   filter_very_large_bb   sunflower/utils/mvg.py:354-362
   nullify_yaw_batch      sunflower/utils/mvg.py:240-251
+  get_points3d           sunflower/utils/mvg.py:387-408   (host, float64: four flops per flower)
 ``squarify_filter_batch`` is the vectorised form used by the predictors; it calls
 the C-ABI ``flope_squarify_filter`` (integer, bit-exact with the scalar pair).
 """
@@ -64,3 +65,14 @@ def nullify_yaw_batch(rotmat):
     from .conversion import nullify_yaw_batch_cuda
     r = torch.as_tensor(np.asarray(rotmat, dtype=np.float32)).cuda()
     return nullify_yaw_batch_cuda(r).cpu().numpy()
+
+
+def get_points3d(uv, Zray, K):
+    """(N,2) pixel coordinates, (N,) ray lengths in metres, (3,3) intrinsics -> (N,3) camera-frame points."""
+    uv = np.asarray(uv, dtype=np.float64)
+    N = uv.shape[0]
+    uv1 = np.hstack((uv, np.ones(N).reshape(-1, 1)))
+    xnyn1 = (np.linalg.inv(K) @ uv1.T).T
+    xnyn1_norm = np.linalg.norm(xnyn1, axis=1)
+    Z = np.asarray(Zray) / xnyn1_norm
+    return xnyn1 * Z.reshape(-1, 1)

@@ -8,16 +8,21 @@ backbone), Procrustes and yaw nullification (fused head kernel).
 
 Out of scope and therefore injected: the detector/segmenter
 (ultralytics YOLO-seg, GroundingDINO + SAM - third-party models whose weights are not
-available offline) and the depth/translation branch (``get_depth_value`` / ``get_points3d``).
-``detector(rgb) -> (boxes (N,4) int, mask (H,W) uint8)`` and ``depth_fn(good_boxes, depth, mask)
--> (xyz (N,3), reliable (N,) bool)`` are constructor keywords; without ``depth_fn`` every box is
-kept and translations are zero.
+available offline): ``detector(rgb) -> (boxes (N,4) int, mask (H,W) uint8)`` is a constructor keyword.
+
+The depth / translation branch (pose_predictor.py:118-135, fast_pose_predictor.py:90-105:
+``get_depth_value`` -> drop unreliable boxes -> ``get_points3d``) runs on the GPU
+(``flope_depth_values``) whenever camera intrinsics are known
+(``intrin_path`` or ``K=``); the raw uint16 depth frame crosses PCIe as is and is scaled on the device.
+``depth_fn(good_boxes, depth_m, mask) -> (xyz (N,3), reliable (N,) bool)`` overrides it; without
+intrinsics and without ``depth_fn`` every box is kept and translations are zero.
 """
 import numpy as np
 import torch
 
 from . import _lib
-from .mvg import filter_very_large_bb
+from .image_manipulation import RELIABLE_MIN_PIXELS
+from .mvg import filter_very_large_bb, get_points3d
 from .posenet import PoseResNet
 
 
@@ -36,9 +41,10 @@ class _PredictorBase:
     CROP = 512                      # the reference's crop side (pose_predictor.py:145)
     INTERP = _lib.INTERP_LANCZOS4   # cv2.INTER_LANCZOS4 (pose_predictor.py:145-146)
     DEPTH_SCALE = 1000.0
+    NEAR_PLANE, FAR_PLANE = 0.1, 2.5
 
     def _init_common(self, device, posenet_path, intrin_path, debug, detector, depth_fn, posenet, max_batch,
-                     crop_hw, interp):
+                     crop_hw, interp, K=None):
         self.device = torch.device(device if device != 'cuda' else 'cuda:0')
         self.debug = debug
         self.detector = detector
@@ -52,6 +58,8 @@ class _PredictorBase:
             if posenet_path is not None:
                 self.posenet.load_state_dict(torch.load(posenet_path, weights_only=True, map_location="cpu"))
         self.K, self.height, self.width = _load_intrinsics(intrin_path)
+        if K is not None:
+            self.K = np.asarray(K, dtype=np.float64)
 
     def _filter_boxes(self, boxes):
         return boxes
@@ -72,13 +80,33 @@ class _PredictorBase:
         if good_bb.shape[0] == 0:
             return None
         xyz = None
+        mask_dev = None
         if self.depth_fn is not None:
             xyz, reliable = self.depth_fn(good_bb, depth.astype(np.float32) / self.DEPTH_SCALE, mask)
             sq_bb = sq_bb[reliable]
             xyz = np.asarray(xyz)[reliable] if len(xyz) == len(reliable) else np.asarray(xyz)
             if sq_bb.shape[0] == 0:
                 return None
-        rot = self.poses_from_boxes(rgb, mask, sq_bb)
+        elif self.K is not None and depth is not None:
+            # pose_predictor.py:118-135 on the device: depth values, reliability filter, lift the box centres to 3-D
+            u = (good_bb[:, 2].astype(np.float64) + good_bb[:, 0]) / 2          # pose_predictor.py:98-99
+            v = (good_bb[:, 3].astype(np.float64) + good_bb[:, 1]) / 2
+            depth = np.asarray(depth)
+            with torch.cuda.device(self.device):
+                mask_dev = torch.from_numpy(np.ascontiguousarray(mask)).to(self.device)
+                if depth.dtype == np.uint16:
+                    d_dev, div = torch.from_numpy(np.ascontiguousarray(depth)).to(self.device), self.DEPTH_SCALE
+                else:
+                    d_dev, div = torch.from_numpy(depth.astype(np.float32) / np.float32(self.DEPTH_SCALE)).to(self.device), None
+                b_dev = torch.from_numpy(good_bb.astype(np.int32)).to(self.device)
+                val, cnt, _ = _lib.depth_values(d_dev, mask_dev, b_dev, self.NEAR_PLANE, self.FAR_PLANE, depth_div=div)
+                reliable = cnt.cpu().numpy() >= RELIABLE_MIN_PIXELS
+                depth_val = val.cpu().numpy()[reliable]
+            sq_bb = sq_bb[reliable]
+            if sq_bb.shape[0] == 0:
+                return None
+            xyz = get_points3d(np.stack([u, v], 1)[reliable], depth_val, self.K)
+        rot = self.poses_from_boxes(rgb, mask if mask_dev is None else mask_dev[None], sq_bb)
         Rt = np.repeat(np.eye(4)[None], rot.shape[0], axis=0)      # fast_pose_predictor.py:142-144
         Rt[:, :3, :3] = rot
         if xyz is not None:
@@ -94,7 +122,10 @@ class _PredictorBase:
         eng = self.posenet.engine
         with torch.cuda.device(self.device):
             frame = torch.from_numpy(np.ascontiguousarray(rgb)).to(self.device, non_blocking=True)[None]
-            msk = None if mask is None else torch.from_numpy(np.ascontiguousarray(mask)).to(self.device)[None]
+            if mask is None or torch.is_tensor(mask):
+                msk = mask
+            else:
+                msk = torch.from_numpy(np.ascontiguousarray(mask)).to(self.device)[None]
             b5 = np.zeros((sq_bb.shape[0], 5), np.int32)
             b5[:, 1:] = sq_bb
             b5 = torch.from_numpy(b5).to(self.device)
@@ -105,23 +136,25 @@ class _PredictorBase:
 class FastPosePredictor(_PredictorBase):
     """sunflower/predictor/fast_pose_predictor.py:19-156 (YOLO-seg front end, depth in mm)."""
     DEPTH_SCALE = 1000.0            # fast_pose_predictor.py:90
+    NEAR_PLANE, FAR_PLANE = 0.1, 2.5    # fast_pose_predictor.py:91-94
 
     def __init__(self, device: str, yolo_path: str = None, posenet_path: str = None, intrin_path: str = None,
                  debug: bool = False, *, detector=None, depth_fn=None, posenet=None, max_batch=64, crop_hw=None,
-                 interp=None):
+                 interp=None, K=None):
         self.yolo_path = yolo_path
         self._init_common(device, posenet_path, intrin_path, debug, detector, depth_fn, posenet, max_batch, crop_hw,
-                          interp)
+                          interp, K)
 
 
 class PosePredictor(_PredictorBase):
     """sunflower/predictor/pose_predictor.py:40-186 (GroundingDINO + SAM front end, depth in 0.1 mm)."""
     DEPTH_SCALE = 10000.0           # pose_predictor.py:118
+    NEAR_PLANE, FAR_PLANE = 0.1, 2.5    # pose_predictor.py:119-122
 
     def __init__(self, device: str, posenet_path: str = None, intrin_path: str = None, debug: bool = False, *,
-                 detector=None, depth_fn=None, posenet=None, max_batch=64, crop_hw=None, interp=None):
+                 detector=None, depth_fn=None, posenet=None, max_batch=64, crop_hw=None, interp=None, K=None):
         self._init_common(device, posenet_path, intrin_path, debug, detector, depth_fn, posenet, max_batch, crop_hw,
-                          interp)
+                          interp, K)
 
     def _filter_boxes(self, boxes):
         return filter_very_large_bb(boxes)      # pose_predictor.py:83

@@ -98,6 +98,24 @@ int flope_infer_frames(flope_engine* e, const uint8_t* d_frames, int n_frames, i
                        const uint8_t* d_masks, const int32_t* d_boxes, int n, int interp, float* d_r9, float* d_R,
                        double* d_R_yaw, void* stream);
 
+/* ---- "next" row N2 of SURVEY.md section 8(f): the depth branch of get_flower_poses ----
+ * Replaces get_depth_value (sunflower/utils/image_manipulation.py:39-96; shrink_mask :21-36), called at
+ * sunflower/predictor/pose_predictor.py:118-121 (depth/10000, near 0.1, far 2.5) and
+ * fast_pose_predictor.py:90-93 (depth/1000).  Stateless (no engine): all buffers are the caller's, on `device`.
+ *   d_depth      (H,W) float32 metres (depth_dtype 0) or uint16 sensor units (depth_dtype 1; metres = raw / depth_div,
+ *                the reference's depth.astype(np.float32) / 10000)
+ *   d_mask       (H,W) uint8 segmentation mask (set where > 128)
+ *   d_boxes      (n,4) int32 xmin,ymin,xmax,ymax - the DETECTOR boxes that survived squarify + in-frame filtering
+ *   erode_k      side of cv2's MORPH_ELLIPSE structuring element (the reference uses 10)
+ *   d_scratch    (H,W) uint8 work buffer (receives the eroded validity mask)
+ *   d_val        (n) float64: mean depth in metres over the box's valid pixels (0 when there is none)
+ *   d_count      (n) int32: number of valid pixels; the reference calls a box reliable when count >= 50
+ * Validity, erosion and counts are exact; the mean is accumulated in fp64 where numpy sums fp32 pairwise
+ * (agreement ~1e-7 relative). */
+int flope_depth_values(int device, const void* d_depth, int depth_dtype, float depth_div, const uint8_t* d_mask, int H, int W,
+                       const int32_t* d_boxes, int n, float near_plane, float far_plane, int erode_k, uint8_t* d_scratch,
+                       double* d_val, int32_t* d_count, void* stream);
+
 /* Number of kernels the last call on this engine launched (bench.py reports it). */
 int flope_engine_last_launches(const flope_engine* e);
 

@@ -16,12 +16,16 @@ The reference (wvu-irl/flope) is pure Python, so the oracle is Python too
   oracle.posenet   PoseResNet (sunflower/models/posenet.py:5-34), eval mode, fp32
   oracle.rotation  procrustes_to_rotmat (sunflower/utils/conversion.py:54-58),
                    nullify_yaw_batch (sunflower/utils/mvg.py:240-251), Rt assembly
-  oracle.pipeline  the composed path frame+mask+boxes -> (N,4,4)
+  oracle.depth     get_depth_value / shrink_mask (sunflower/utils/image_manipulation.py:21-96),
+                   get_points3d (sunflower/utils/mvg.py:387-408) - the depth / translation branch
+  oracle.pipeline  the composed path frame+mask+boxes(+depth, K) -> (N,4,4)
 
 Pinning status (also in DESIGN.md):
   * boxes, PoseResNet, nullify_yaw_batch, procrustes_to_rotmat's reshape: PINNED
     against the reference's own functions imported from /root/reference
     (tests/golden/make_golden.py; fixtures committed under tests/golden/).
+  * get_depth_value / shrink_mask / get_points3d: PINNED against the reference's own
+    functions (tests/golden/depth.npz; matplotlib / plotly stubbed for the import).
   * cv2.resize arithmetic: pinned against the cv2 build in this image (4.13.0;
     the reference pins 4.10.0.84).
   * roma.special_procrustes (roma==1.5.1, environment.yml:214) is a third-party

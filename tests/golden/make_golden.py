@@ -104,6 +104,39 @@ def main():
                                            sd["base.fc.0.weight"].flatten()[:16].numpy(),
                                            sd["fc_rot.bias"].numpy()])
     np.savez_compressed(os.path.join(HERE, "posenet_seed0.npz"), **out)
+    # ---- depth branch: get_depth_value (image_manipulation.py:39-96) + get_points3d (mvg.py:387-408) ----
+    for m in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.cm", "matplotlib.colors", "plotly",
+              "plotly.graph_objects", "plotly.express", "plotly.subplots", "plyfile", "icecream", "mpl_toolkits",
+              "mpl_toolkits.mplot3d"):
+        sys.modules.setdefault(m, mock.MagicMock())          # plotting / IO modules image_manipulation.py drags in
+    from sunflower.utils import image_manipulation as ref_im
+    drng = np.random.default_rng(77)
+    dH, dW = 360, 640
+    yy, xx = np.mgrid[0:dH, 0:dW]
+    raw = (3000 + 2500 * np.sin(xx / 37.0) * np.cos(yy / 23.0) + drng.integers(-40, 40, (dH, dW))).astype(np.uint16)
+    raw[drng.random((dH, dW)) < 0.02] = 0                                   # sensor holes
+    raw[:, 600:] = 40000                                                    # beyond the far plane
+    dmask = np.zeros((dH, dW), np.uint8)
+    for cx, cy, rad in ((120, 100, 60), (330, 200, 90), (520, 90, 45), (60, 300, 30), (600, 330, 25), (250, 40, 9)):
+        dmask[(xx - cx) ** 2 + (yy - cy) ** 2 <= rad * rad] = 255
+    dmask[drng.random((dH, dW)) < 0.003] = 0                                # pinholes: erosion grows them
+    dboxes = np.array([[60, 40, 180, 160], [240, 110, 420, 290], [475, 45, 565, 135], [30, 270, 90, 330],
+                       [575, 305, 625, 355], [241, 31, 259, 49], [0, 0, 40, 40], [300, 170, 360, 230],
+                       [0, 0, 640, 360], [610, 0, 640, 30]], np.int16)
+    Kmat = np.array([[430.0, 0, 318.5], [0, 431.5, 181.2], [0, 0, 1]])
+    dout = {"raw": raw, "mask": dmask, "boxes": dboxes, "K": Kmat}
+    for tag, div, far in (("pose", 10000.0, 2.5), ("fast", 1000.0, 3.0)):
+        depth_m = raw.astype(np.float32) / div                              # pose_predictor.py:118 / fast_pose_predictor.py:90
+        val, rel, _ = ref_im.get_depth_value(dboxes, depth_m.copy(), dmask, near_plane=0.1, far_plane=far)
+        uv = np.stack([(dboxes[:, 2].astype(np.float64) + dboxes[:, 0]) / 2, (dboxes[:, 3].astype(np.float64) + dboxes[:, 1]) / 2], 1)
+        dout[f"val_{tag}"] = np.asarray(val, np.float64)
+        dout[f"rel_{tag}"] = rel
+        dout[f"xyz_{tag}"] = ref_mvg.get_points3d(uv, np.asarray(val, np.float64), Kmat)
+        dout[f"div_{tag}"] = np.array(div)
+        dout[f"far_{tag}"] = np.array(far)
+    seg = np.logical_and(dmask > 128, np.logical_and(raw.astype(np.float32) / 10000.0 > 0.1, raw.astype(np.float32) / 10000.0 < 2.5))
+    dout["eroded_pose"] = ref_im.shrink_mask(seg, 10)
+    np.savez_compressed(os.path.join(HERE, "depth.npz"), **dout)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

@@ -1,0 +1,108 @@
+"""GPU parity of the depth branch (flope_depth_values / get_depth_value mirror / predictors with intrinsics) against
+the reference's own outputs (tests/golden/depth.npz) and the oracle.  Validity, erosion and pixel counts are exact;
+the per-box mean is fp64-accumulated on the device where numpy sums float32 pairwise: tolerance 2e-6 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import depth as od
+
+pytestmark = pytest.mark.gpu
+RTOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "depth.npz"))
+
+
+@pytest.mark.parametrize("tag", ["pose", "fast"])
+@pytest.mark.parametrize("as_u16", [True, False])
+def test_depth_values_match_reference_golden(cuda_lib, g, tag, as_u16):
+    div, far = float(g[f"div_{tag}"]), float(g[f"far_{tag}"])
+    mask = torch.from_numpy(g["mask"]).cuda()
+    boxes = torch.from_numpy(g["boxes"].astype(np.int32)).cuda()
+    if as_u16:
+        d = torch.from_numpy(g["raw"]).cuda()
+        val, cnt, eroded = cuda_lib.depth_values(d, mask, boxes, 0.1, far, depth_div=div)
+    else:
+        d = torch.from_numpy(g["raw"].astype(np.float32) / div).cuda()
+        val, cnt, eroded = cuda_lib.depth_values(d, mask, boxes, 0.1, far)
+    torch.cuda.synchronize()
+    assert np.array_equal(cnt.cpu().numpy() >= 50, g[f"rel_{tag}"])
+    np.testing.assert_allclose(val.cpu().numpy(), g[f"val_{tag}"], rtol=RTOL, atol=0)
+    if tag == "pose":
+        assert np.array_equal(eroded.cpu().numpy() > 0, g["eroded_pose"])
+    # pixel counts against the oracle's erosion
+    dm = g["raw"].astype(np.float32) / div
+    seg = od.shrink_mask(np.logical_and(g["mask"] > 128, np.logical_and(dm > 0.1, dm < far)), 10)
+    want_cnt = [int(seg[b[1]:b[3], b[0]:b[2]].sum()) for b in g["boxes"]]
+    assert cnt.cpu().numpy().tolist() == want_cnt
+
+
+def test_get_depth_value_mirror_and_erosion_sizes(cuda_lib, g):
+    from flope_b200 import image_manipulation as im
+    from flope_b200 import mvg
+    depth_m = g["raw"].astype(np.float32) / 10000.0
+    keep = depth_m.copy()
+    val, rel, vis = im.get_depth_value(g["boxes"], depth_m, g["mask"], near_plane=0.1, far_plane=2.5)
+    assert vis is None and val.dtype == np.float64 and rel.dtype == bool
+    assert np.array_equal(depth_m, keep)                         # unlike the reference, the argument is left alone
+    assert np.array_equal(rel, g["rel_pose"])
+    np.testing.assert_allclose(val, g["val_pose"], rtol=RTOL)
+    xyz = mvg.get_points3d(od.box_centres(g["boxes"]), val, g["K"])
+    np.testing.assert_allclose(xyz, g["xyz_pose"], rtol=RTOL, atol=1e-12)
+    rng = np.random.default_rng(4)
+    for k in (1, 2, 3, 5, 10, 11, 31):
+        m = rng.random((97, 131)) > 0.05
+        assert np.array_equal(im.shrink_mask(m, k), od.shrink_mask(m, k)), k
+    with pytest.raises(cuda_lib.FlopeError):
+        im.get_depth_value(g["boxes"], depth_m, g["mask"], vis=True)
+    with pytest.raises(cuda_lib.FlopeError):
+        im.shrink_mask(np.ones((8, 8), bool), 33)
+
+
+def test_empty_and_ragged_boxes(cuda_lib, g):
+    d = torch.from_numpy(g["raw"]).cuda()
+    mask = torch.from_numpy(g["mask"]).cuda()
+    val, cnt, _ = cuda_lib.depth_values(d, mask, torch.zeros((0, 4), dtype=torch.int32, device="cuda"), 0.1, 2.5, depth_div=10000.0)
+    assert val.shape == (0,) and cnt.shape == (0,)
+    # degenerate / partly out-of-frame boxes are clipped to the frame like numpy slicing clips the upper bounds
+    boxes = torch.tensor([[100, 80, 100, 200], [500, 300, 900, 700], [630, 350, 640, 360]], dtype=torch.int32, device="cuda")
+    val, cnt, eroded = cuda_lib.depth_values(d, mask, boxes, 0.1, 2.5, depth_div=10000.0)
+    e = eroded.cpu().numpy() > 0
+    assert cnt.cpu().numpy().tolist() == [0, int(e[300:360, 500:640].sum()), int(e[350:360, 630:640].sum())]
+    assert float(val[0]) == 0.0
+
+
+@pytest.mark.parametrize("cls_name,scale", [("PosePredictor", 10000.0), ("FastPosePredictor", 1000.0)])
+def test_predictors_with_intrinsics_fill_translation(cuda_lib, g, cls_name, scale):
+    """Full drop-in call: detector boxes + uint16 depth + K -> (N,4,4) with rotations AND translations, unreliable boxes
+    dropped, against the oracle pipeline (fast_pose_predictor.py:66-156 / pose_predictor.py:83-186)."""
+    from flope_b200 import predictor as P, synth
+    from flope_b200.posenet import PoseResNet
+    from oracle import pipeline as opipe, posenet as onet, resize as ores, rotation as orot
+    net = onet.build(synth.WEIGHT_SEED)
+    m = PoseResNet(device="cuda:0", max_batch=16, crop_hw=224)
+    m.load_state_dict(net.state_dict())
+    rng = np.random.default_rng(9)
+    frame = rng.integers(0, 256, g["mask"].shape + (3,), dtype=np.uint8)
+    raw = g["raw"] if scale == 10000.0 else (g["raw"] // 10).astype(np.uint16)
+    det = g["boxes"][[0, 1, 2, 3, 5, 7]].astype(np.int16)        # box 5: fewer than 50 valid pixels -> dropped
+    cls = getattr(P, cls_name)
+    pred = cls("cuda:0", detector=lambda rgb: (det, g["mask"]), posenet=m, crop_hw=224, interp=ores.BILINEAR, K=g["K"])
+    Rt = pred.get_flower_poses(frame, raw)
+    from oracle import boxes as obox
+    det_in = obox.filter_very_large_bb(det) if cls_name == "PosePredictor" else det      # pose_predictor.py:83
+    want = opipe.run(net, frame, g["mask"], det_in, size=224, interp=ores.BILINEAR, depth=raw, K=g["K"], depth_scale=scale,
+                     far_plane=2.5)
+    assert want["reliable"].sum() < len(det_in)
+    assert Rt.shape == want["Rt"].shape and Rt.dtype == np.float64
+    np.testing.assert_allclose(Rt[:, :3, 3], want["Rt"][:, :3, 3], rtol=RTOL, atol=1e-12)
+    assert np.all(Rt[:, :3, 3][:, 2] > 0.05)
+    assert orot.geodesic_deg(Rt[:, :3, :3], want["Rt"][:, :3, :3]).mean() <= 0.5
+    # all boxes unreliable -> None, like the reference (pose_predictor.py:129-130)
+    none = cls("cuda:0", detector=lambda rgb: (det, np.zeros_like(g["mask"])), posenet=m, crop_hw=224, interp=ores.BILINEAR, K=g["K"])
+    assert none.get_flower_poses(frame, raw) is None
