@@ -20,7 +20,7 @@ SYMBOLS = [
     "flope_engine_load_weights", "flope_squarify_filter", "flope_roi_crop", "flope_posenet_forward",
     "flope_pose_head", "flope_nullify_yaw", "flope_infer_frames", "flope_engine_last_launches",
     "flope_debug_activation", "flope_debug_normalise_lut", "flope_debug_set",
-    "flope_engine_profile", "flope_engine_profile_read", "flope_depth_values",
+    "flope_engine_profile", "flope_engine_profile_read", "flope_depth_values", "flope_yolo_mask",
 ]
 
 
@@ -65,6 +65,8 @@ def lib():
         L.flope_depth_values.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                          C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]
+        L.flope_yolo_mask.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -119,6 +121,23 @@ def depth_values(depth, mask, boxes, near_plane, far_plane, depth_div=None, erod
                                        _ptr(boxes.contiguous()), n, float(near_plane), float(far_plane), int(erode_k),
                                        _ptr(scratch), _ptr(val), _ptr(cnt), _stream()))
     return val, cnt, scratch
+
+
+def yolo_mask(masks, H, W):
+    """flope_yolo_mask: (n,h,w) float32 CUDA instance masks -> (H,W) uint8 CUDA mask (0/255 union, cv2-exact resize)."""
+    import torch
+    if not masks.is_cuda:
+        raise FlopeError("yolo_mask needs CUDA tensors (there is no CPU fallback)")
+    masks = masks.to(torch.float32).contiguous()
+    n, h, w = masks.shape
+    dev = masks.device
+    small = torch.empty((h, w), dtype=torch.uint8, device=dev)
+    out = torch.empty((H, W), dtype=torch.uint8, device=dev)
+    tables = torch.empty(((W + H) * 8,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().flope_yolo_mask(dev.index or 0, _ptr(masks), n, h, w, _ptr(small), _ptr(out), int(H), int(W),
+                                    _ptr(tables), _stream()))
+    return out
 
 
 class Engine:

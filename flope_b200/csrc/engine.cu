@@ -18,6 +18,7 @@
 #include "../../include/flope_b200.h"
 #include "conv_igemm.cuh"
 #include "depth.cuh"
+#include "mask_post.cuh"
 #include "pointwise.cuh"
 #include "pose_head.cuh"
 #include "roi_crop.cuh"
@@ -924,6 +925,27 @@ int flope_depth_values(int device, const void* d_depth, int depth_dtype, float d
   dim3 grid((W + kErodeTileW - 1) / kErodeTileW, (H + kErodeTileH - 1) / kErodeTileH);
   erode_valid_kernel<<<grid, 256, 0, st>>>(dp);
   if (n > 0) box_depth_kernel<<<n, 256, 0, st>>>(dp, d_boxes, n, d_val, d_count);
+  CUDA_TRY(cudaGetLastError());
+  return FLOPE_OK;
+}
+
+int flope_yolo_mask(int device, const float* d_masks, int n, int h, int w, uint8_t* d_small, uint8_t* d_out, int H, int W,
+                    void* d_tables, void* stream) {
+  if (!d_small || !d_out || !d_tables || (n > 0 && !d_masks)) return fail(FLOPE_EINVAL, "NULL argument");
+  if (n < 0 || h < 1 || w < 1 || H < 1 || W < 1) return fail(FLOPE_EINVAL, "bad sizes");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  // d_tables: (W + H) int32 source indices followed by (W + H) x 2 int16 coefficients
+  int* xofs = reinterpret_cast<int*>(d_tables);
+  int* yofs = xofs + W;
+  short* xcoef = reinterpret_cast<short*>(yofs + H);
+  short* ycoef = xcoef + 2 * (size_t)W;
+  const long long hw = (long long)h * w;
+  merge_instance_masks_kernel<<<grid_for(hw, 256), 256, 0, st>>>(d_masks, n, hw, d_small);
+  linear_table_kernel<<<(W + 127) / 128, 128, 0, st>>>(W, w, 0, xofs, xcoef);
+  linear_table_kernel<<<(H + 127) / 128, 128, 0, st>>>(H, h, 1, yofs, ycoef);
+  dim3 blk(32, 8), grid((W + 31) / 32, (H + 7) / 8);
+  resize_linear_u8_kernel<<<grid, blk, 0, st>>>(d_small, h, w, d_out, H, W, xofs, xcoef, yofs, ycoef);
   CUDA_TRY(cudaGetLastError());
   return FLOPE_OK;
 }

@@ -8,7 +8,11 @@ backbone), Procrustes and yaw nullification (fused head kernel).
 
 Out of scope and therefore injected: the detector/segmenter
 (ultralytics YOLO-seg, GroundingDINO + SAM - third-party models whose weights are not
-available offline): ``detector(rgb) -> (boxes (N,4) int, mask (H,W) uint8)`` is a constructor keyword.
+available offline): ``detector(rgb) -> (boxes (N,4) int, mask (H,W) uint8 ndarray or CUDA tensor)`` is a
+constructor keyword.  ``FastPosePredictor(yolo=callable)`` instead takes the raw YOLO-seg model call
+(``yolo(image)[0].masks.data`` / ``.boxes.xyxy`` like ultralytics) and does the reference's
+``get_bbox_mask`` post-processing on the GPU (``flope_yolo_mask``): instance masks
+are merged and resized to the frame with cv2-exact bilinear arithmetic without leaving the device.
 
 The depth / translation branch (pose_predictor.py:118-135, fast_pose_predictor.py:90-105:
 ``get_depth_value`` -> drop unreliable boxes -> ``get_points3d``) runs on the GPU
@@ -68,6 +72,8 @@ class _PredictorBase:
         if self.detector is None:
             raise _lib.FlopeError("no detector injected: pass detector=callable(rgb)->(boxes, mask)")
         boxes, mask = self.detector(rgb)
+        if torch.is_tensor(mask) and self.depth_fn is not None:
+            mask = mask.cpu().numpy()               # an injected depth function gets the reference's numpy mask
         boxes = np.asarray(boxes)
         if boxes.shape[0] == 0:
             return None
@@ -93,7 +99,7 @@ class _PredictorBase:
             v = (good_bb[:, 3].astype(np.float64) + good_bb[:, 1]) / 2
             depth = np.asarray(depth)
             with torch.cuda.device(self.device):
-                mask_dev = torch.from_numpy(np.ascontiguousarray(mask)).to(self.device)
+                mask_dev = mask.to(self.device) if torch.is_tensor(mask) else torch.from_numpy(np.ascontiguousarray(mask)).to(self.device)
                 if depth.dtype == np.uint16:
                     d_dev, div = torch.from_numpy(np.ascontiguousarray(depth)).to(self.device), self.DEPTH_SCALE
                 else:
@@ -106,6 +112,8 @@ class _PredictorBase:
             if sq_bb.shape[0] == 0:
                 return None
             xyz = get_points3d(np.stack([u, v], 1)[reliable], depth_val, self.K)
+        if mask_dev is None and torch.is_tensor(mask):
+            mask_dev = mask.to(self.device)
         rot = self.poses_from_boxes(rgb, mask if mask_dev is None else mask_dev[None], sq_bb)
         Rt = np.repeat(np.eye(4)[None], rot.shape[0], axis=0)      # fast_pose_predictor.py:142-144
         Rt[:, :3, :3] = rot
@@ -140,10 +148,27 @@ class FastPosePredictor(_PredictorBase):
 
     def __init__(self, device: str, yolo_path: str = None, posenet_path: str = None, intrin_path: str = None,
                  debug: bool = False, *, detector=None, depth_fn=None, posenet=None, max_batch=64, crop_hw=None,
-                 interp=None, K=None):
+                 interp=None, K=None, yolo=None):
         self.yolo_path = yolo_path
+        self.yolo = yolo
+        if detector is None and yolo is not None:
+            detector = self._bbox_mask_device
         self._init_common(device, posenet_path, intrin_path, debug, detector, depth_fn, posenet, max_batch, crop_hw,
                           interp, K)
+
+    def _bbox_mask_device(self, image):
+        """fast_pose_predictor.py:44-57 with the mask kept on the GPU: (bbox (n,4) int16 ndarray, mask (H,W) uint8 CUDA tensor)."""
+        H, W, _ = image.shape
+        results = self.yolo(image)
+        masks = results[0].masks.data
+        mask = _lib.yolo_mask(torch.as_tensor(masks).to(self.device), H, W)
+        bbox = torch.as_tensor(results[0].boxes.xyxy).cpu().numpy().astype(np.int16)
+        return bbox, mask
+
+    def get_bbox_mask(self, image):
+        """Same contract as the reference method: (bbox (n,4) int16, mask (H,W) uint8), both numpy."""
+        bbox, mask = self._bbox_mask_device(image)
+        return bbox, mask.cpu().numpy()
 
 
 class PosePredictor(_PredictorBase):

@@ -116,6 +116,14 @@ int flope_depth_values(int device, const void* d_depth, int depth_dtype, float d
                        const int32_t* d_boxes, int n, float near_plane, float far_plane, int erode_k, uint8_t* d_scratch,
                        double* d_val, int32_t* d_count, void* stream);
 
+/* ---- "next" row N1 of SURVEY.md section 8(f): YOLO-seg post-processing ----
+ * Replaces the mask half of FastPosePredictor.get_bbox_mask (sunflower/predictor/fast_pose_predictor.py:44-57):
+ *   mask = uint8(clip(sum(masks, 0), 0, 1) * 255);  mask = cv2.resize(mask, (W, H))          # INTER_LINEAR, bit-exact
+ * d_masks (n,h,w) float32 instance masks (n may be 0: all-zero mask), d_small (h,w) uint8 scratch, d_out (H,W) uint8,
+ * d_tables scratch of (W + H) * 8 bytes.  Stateless; everything stays on `device`. */
+int flope_yolo_mask(int device, const float* d_masks, int n, int h, int w, uint8_t* d_small, uint8_t* d_out, int H, int W,
+                    void* d_tables, void* stream);
+
 /* Number of kernels the last call on this engine launched (bench.py reports it). */
 int flope_engine_last_launches(const flope_engine* e);
 

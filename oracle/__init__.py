@@ -18,6 +18,8 @@ The reference (wvu-irl/flope) is pure Python, so the oracle is Python too
                    nullify_yaw_batch (sunflower/utils/mvg.py:240-251), Rt assembly
   oracle.depth     get_depth_value / shrink_mask (sunflower/utils/image_manipulation.py:21-96),
                    get_points3d (sunflower/utils/mvg.py:387-408) - the depth / translation branch
+  oracle.detector_post  the post-processing half of FastPosePredictor.get_bbox_mask
+                   (sunflower/predictor/fast_pose_predictor.py:48-57)
   oracle.pipeline  the composed path frame+mask+boxes(+depth, K) -> (N,4,4)
 
 Pinning status (also in DESIGN.md):
@@ -26,6 +28,8 @@ Pinning status (also in DESIGN.md):
     (tests/golden/make_golden.py; fixtures committed under tests/golden/).
   * get_depth_value / shrink_mask / get_points3d: PINNED against the reference's own
     functions (tests/golden/depth.npz; matplotlib / plotly stubbed for the import).
+  * get_bbox_mask post-processing: PINNED against the reference method itself run with a stub
+    detector (tests/golden/yolo_post.npz).
   * cv2.resize arithmetic: pinned against the cv2 build in this image (4.13.0;
     the reference pins 4.10.0.84).
   * roma.special_procrustes (roma==1.5.1, environment.yml:214) is a third-party

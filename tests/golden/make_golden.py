@@ -137,6 +137,32 @@ def main():
     seg = np.logical_and(dmask > 128, np.logical_and(raw.astype(np.float32) / 10000.0 > 0.1, raw.astype(np.float32) / 10000.0 < 2.5))
     dout["eroded_pose"] = ref_im.shrink_mask(seg, 10)
     np.savez_compressed(os.path.join(HERE, "depth.npz"), **dout)
+    # ---- YOLO-seg post-processing: the real FastPosePredictor.get_bbox_mask (fast_pose_predictor.py:44-57) on an
+    #      instance whose detector is a stub (ultralytics and the other heavy imports are absent here) ----
+    for m in ("ultralytics", "hydra", "omegaconf", "filterpy", "filterpy.kalman", "shapely", "shapely.geometry", "tyro"):
+        sys.modules.setdefault(m, mock.MagicMock())
+    from sunflower.predictor.fast_pose_predictor import FastPosePredictor as RefFast
+    yrng = np.random.default_rng(31)
+    yout = {}
+    for tag, (h, w, H, W, n) in {"a": (384, 640, 1080, 1920, 5), "b": (160, 256, 360, 640, 3), "c": (96, 128, 97, 131, 2),
+                                 "d": (384, 640, 192, 320, 4)}.items():
+        yy, xx = np.mgrid[0:h, 0:w]
+        masks = np.zeros((n, h, w), np.float32)
+        for k in range(n):
+            cx, cy, rad = yrng.integers(0, w), yrng.integers(0, h), yrng.integers(5, h // 3)
+            masks[k][(xx - cx) ** 2 + (yy - cy) ** 2 <= rad * rad] = 1.0
+        boxes = (yrng.random((n, 4)) * [W, H, W, H]).astype(np.float32)
+        boxes[0] = [0.0, 0.99, W - 0.01, H - 0.5]
+        res = types.SimpleNamespace(masks=types.SimpleNamespace(data=torch.from_numpy(masks)),
+                                    boxes=types.SimpleNamespace(xyxy=torch.from_numpy(boxes)))
+        inst = object.__new__(RefFast)
+        inst.yolo = lambda img, _r=res: [_r]
+        bbox, mask = inst.get_bbox_mask(np.zeros((H, W, 3), np.uint8))
+        yout[f"masks_{tag}"] = masks.astype(np.uint8)
+        yout[f"boxes_{tag}"] = boxes
+        yout[f"bbox_{tag}"] = bbox
+        yout[f"mask_{tag}"] = mask
+    np.savez_compressed(os.path.join(HERE, "yolo_post.npz"), **yout)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

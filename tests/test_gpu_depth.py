@@ -106,3 +106,46 @@ def test_predictors_with_intrinsics_fill_translation(cuda_lib, g, cls_name, scal
     # all boxes unreliable -> None, like the reference (pose_predictor.py:129-130)
     none = cls("cuda:0", detector=lambda rgb: (det, np.zeros_like(g["mask"])), posenet=m, crop_hw=224, interp=ores.BILINEAR, K=g["K"])
     assert none.get_flower_poses(frame, raw) is None
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_yolo_mask_postprocessing_bit_exact(cuda_lib, golden_dir, tag):
+    """flope_yolo_mask against the reference's own get_bbox_mask outputs: up- and down-scaling, odd sizes."""
+    y = np.load(os.path.join(golden_dir, "yolo_post.npz"))
+    H, W = y[f"mask_{tag}"].shape
+    masks = torch.from_numpy(y[f"masks_{tag}"].astype(np.float32)).cuda()
+    got = cuda_lib.yolo_mask(masks, H, W)
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), y[f"mask_{tag}"])
+    empty = cuda_lib.yolo_mask(torch.zeros((0,) + tuple(masks.shape[1:]), device="cuda"), H, W)
+    assert int(empty.max()) == 0
+
+
+def test_fast_predictor_with_raw_yolo_results(cuda_lib, golden_dir, g):
+    """FastPosePredictor(yolo=...) does get_bbox_mask on the device and feeds the mask tensor straight into the depth
+    and ROI kernels; the public get_bbox_mask keeps the reference's numpy contract."""
+    import types
+    from flope_b200 import predictor as P, synth
+    from flope_b200.posenet import PoseResNet
+    from oracle import detector_post as op, pipeline as opipe, posenet as onet, resize as ores, rotation as orot
+    y = np.load(os.path.join(golden_dir, "yolo_post.npz"))
+    masks = torch.from_numpy(y["masks_b"].astype(np.float32))
+    boxes = torch.tensor([[60.4, 40.9, 180.2, 160.7], [240.0, 110.5, 420.9, 290.1], [475.3, 45.0, 565.8, 135.9]])
+    res = [types.SimpleNamespace(masks=types.SimpleNamespace(data=masks.cuda()), boxes=types.SimpleNamespace(xyxy=boxes.cuda()))]
+    net = onet.build(synth.WEIGHT_SEED)
+    m = PoseResNet(device="cuda:0", max_batch=8, crop_hw=224)
+    m.load_state_dict(net.state_dict())
+    pred = P.FastPosePredictor("cuda:0", yolo=lambda img: res, posenet=m, crop_hw=224, interp=ores.BILINEAR, K=g["K"])
+    frame = np.random.default_rng(2).integers(0, 256, (360, 640, 3), dtype=np.uint8)
+    bbox, mask = pred.get_bbox_mask(frame)
+    want_bbox, want_mask = op.bbox_mask_from_results(masks, boxes, 360, 640)
+    assert bbox.dtype == np.int16 and np.array_equal(bbox, want_bbox) and np.array_equal(mask, want_mask)
+    raw = (g["raw"] // 10).astype(np.uint16)
+    Rt = pred.get_flower_poses(frame, raw)
+    want = opipe.run(net, frame, want_mask, want_bbox, size=224, interp=ores.BILINEAR, depth=raw, K=g["K"], depth_scale=1000.0)
+    if want is None:
+        assert Rt is None
+    else:
+        assert Rt.shape == want["Rt"].shape
+        np.testing.assert_allclose(Rt[:, :3, 3], want["Rt"][:, :3, 3], rtol=RTOL, atol=1e-12)
+        assert orot.geodesic_deg(Rt[:, :3, :3], want["Rt"][:, :3, :3]).mean() <= 0.5

@@ -42,3 +42,16 @@ def test_ellipse_spans_match_cv2(k):
         want = np.zeros(k, np.uint8)
         want[j1:j2] = 1
         assert np.array_equal(el[i], want), (k, i)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_yolo_postprocessing_oracle_matches_reference(golden_dir, tag):
+    """oracle/detector_post.py against the outputs of the reference's own get_bbox_mask (tests/golden/yolo_post.npz)."""
+    import torch
+    from oracle import detector_post as op
+    y = np.load(os.path.join(golden_dir, "yolo_post.npz"))
+    H, W = y[f"mask_{tag}"].shape
+    bbox, mask = op.bbox_mask_from_results(torch.from_numpy(y[f"masks_{tag}"].astype(np.float32)),
+                                           torch.from_numpy(y[f"boxes_{tag}"]), H, W)
+    assert bbox.dtype == np.int16 and np.array_equal(bbox, y[f"bbox_{tag}"])
+    assert np.array_equal(mask, y[f"mask_{tag}"])
