@@ -37,12 +37,16 @@ def gather_rows(local, n_total, group=None):
     return out[:n_total]
 
 
-def run_sharded(fn, n_total, micro_batch, group=None):
-    """Run fn(lo, hi) -> (hi-lo, ...) tensor over this rank's range in micro-batches and gather everything."""
+def run_sharded(fn, n_total, micro_batch, group=None, join=None):
+    """Run fn(lo, hi) -> (hi-lo, ...) tensor over this rank's range in micro-batches and gather everything.
+    `join` (optional) is called once all micro-batches are queued and before their results are concatenated - e.g.
+    EnginePool.join when fn submits its work to side streams."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     lo, hi = shard_range(n_total, rank, world)
     parts = [fn(s, min(hi, s + micro_batch)) for s in range(lo, hi, micro_batch)]
+    if join is not None:
+        join()
     local = torch.cat(parts) if parts else None
     if local is None:                       # empty shard: still take part in the collective
         probe = fn(0, 0)
