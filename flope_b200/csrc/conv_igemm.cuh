@@ -33,7 +33,8 @@
 //
 // POOL (stem): conv + BN + ReLU + 3x3/s2 max-pool in one kernel, the 112x112x64 stem tensor never reaches HBM.
 // Sub-tile mt of a tile is one *conv row* (lane = column, so W + 2 <= 128) and a tile is four consecutive rows
-// 4t..4t+3 of one crop; a work item is a quarter of a crop (H/4 rows), processed top to bottom by one CTA:
+// 4t..4t+3 of one crop; a work item is a band of a crop (a quarter; an eighth-ish for small batches), walked top to
+// bottom by one CTA:
 //   vertical max  : the four rows of a column sit in the same TMEM lane -> pure register work; pooled row 2t
 //                   needs conv row 4t-1, which the thread carries over from the previous tile (a one-row
 //                   "carry" tile opens every quarter)
@@ -53,7 +54,6 @@ constexpr int kEpiWarps = 16;                  // 4 per TMEM lane quarter
 constexpr int kConvThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxASlots = 8;
 constexpr int kMaxBSlots = 16;
-constexpr int kPoolSplit = 4;                  // POOL: work items per crop (row quarters)
 constexpr int kPoolXchBytes = 2 * 4 * 4 * 16 * 4;
 
 enum OutMode : int { OUT_PLAIN = 0, OUT_PARITY = 1, OUT_F32_ROWS = 2 };
@@ -91,7 +91,8 @@ struct ConvParams {
   int res_base, res_Hp, res_Wp;
   // ---- smem ring sizes ----
   int n_a_slots, n_b_slots;
-  int pool_rows;               // POOL: conv rows per work item (H / kPoolSplit, a multiple of 4); 0 otherwise
+  int pool_rows;               // POOL: conv rows per work item (a multiple of 4 that divides H); 0 otherwise
+  int pool_split;              // POOL: work items per crop (H / pool_rows)
   int b_resident;              // all weight tiles fit the ring and n_n_tiles == 1: load them once per CTA
   // ---- second A source: K groups >= first_group2 are read from in2 (the projection shortcut of a
   //      ResNet block folded into its conv2 as extra K: same position space, shift 0) ----
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   auto tile_first_pos = [&](int w, int tt) -> int {
     if (!POOL) return (w / p.n_n_tiles) * TILE_POS + (PAIR ? (int)rank * TM : 0);
     const int unit = PAIR ? 2 * w + (int)rank : w;
-    const int n = unit / kPoolSplit, q = unit - n * kPoolSplit;
+    const int n = unit / p.pool_split, q = unit - n * p.pool_split;
     return (n * p.Hp + q * p.pool_rows + 4 * (tt - 1)) * p.Wp;
   };
 
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       if constexpr (POOL) {
         // ---------- stem: conv + BN + ReLU rows -> 3x3/s2 max-pool, two pooled rows per four-row tile ----------
         const int unit = PAIR ? 2 * w + (int)rank : w;
-        const int n = unit / kPoolSplit, q = unit - n * kPoolSplit;
+        const int n = unit / p.pool_split, q = unit - n * p.pool_split;
         const int col = quarter * 32 + lane;                  // conv column of this thread
         const bool col_ok = col < p.W;
         float bias16[16];

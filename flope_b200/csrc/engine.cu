@@ -130,7 +130,7 @@ cudaError_t conv_launch_t(const ConvParams& p, dim3 grid, size_t smem, cudaStrea
   X(64, 4, 4, false, false, 0) X(128, 2, 4, false, false, 0)                                                   \
   X(64, 4, 1, false, false, 16) X(64, 4, 1, true, false, 16)                                                   \
   /* CTA pair */                                                                                               \
-  X(64, 4, 4, false, true, 0) X(128, 2, 4, false, true, 0) X(256, 1, 4, false, true, 0)                        \
+  X(64, 4, 4, false, true, 0) X(128, 2, 4, false, true, 0) X(256, 1, 4, false, true, 0) X(64, 1, 4, false, true, 0) \
   X(64, 4, 1, false, true, 16) X(64, 4, 1, true, true, 16)
 
 cudaError_t conv_set_all_attrs() {
@@ -164,6 +164,7 @@ struct flope_engine {
   std::vector<ConvLayer> layers;
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
   int roi_strip = 14;                            // output rows per CTA of the bilinear ROI kernel (even; crops below 448 px)
+  bool small_tiles = true;                       // latency-oriented tiles when max_batch is too small to fill the SMs
   bool use_pdl = true;                           // programmatic dependent launch between the backbone kernels
   bool use_pair = true;                          // CTA-pair (cta_group::2) conv kernels; flope_debug_set "pair" 0 selects the single-CTA ones
   bool fuse_pool = false;                        // stem conv + max-pool in one kernel (default whenever the crop side allows it)
@@ -350,13 +351,25 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
   L.n_tile = L.cout >= 128 ? 128 : 64;
   if (L.pair && L.cout >= 256) L.n_tile = 256; // M = 256 x N = 256 MMAs: 8 KB of operand reads per SM per 128 tensor cycles
   L.mt = 256 / L.n_tile;                       // 2 stages x 256 columns = all 512 TMEM columns
+  if (L.pair && !L.pool && L.kind != K_STEM && e->small_tiles) {
+    // small batches (streaming: a handful of flowers per frame): with the throughput tiles a layer is a few work
+    // items whose serial MMA chain (up to 288 K-steps at N = 256) is the whole latency.  128-position x 64-channel
+    // tiles give 4-16x more items and chains of 36-288 short MMAs.
+    const long long npos = (long long)e->max_batch * p.Hp * p.Wp;
+    const long long items = (npos + 256 * L.mt - 1) / (256 * L.mt) * (L.cout / L.n_tile);
+    if (items < e->num_sms / 4) { L.n_tile = 64; L.mt = 1; }
+  }
   const int nb_rows = L.pair ? L.n_tile / 2 : L.n_tile;   // weight rows per CTA and tile
   size_t pool_smem = 0;
   int span = L.mt * 128;                       // positions of the halo tile one tile covers (without the halo)
   if (L.pool) {
     // sub-tile = one conv row (lane = column), tile = four rows, work item = a quarter of a crop
-    if (p.Wp > 128 || p.H % (4 * kPoolSplit)) return fail(FLOPE_EINVAL, "fused stem pooling needs S/2+2 <= 128 and S % 32 == 0");
-    p.pool_rows = p.H / kPoolSplit;
+    if (p.Wp > 128 || p.H % 16) return fail(FLOPE_EINVAL, "fused stem pooling needs S/2+2 <= 128 and S % 32 == 0");
+    // a work item is a band of pool_rows conv rows (a quarter of the crop; 8 rows when the batch is too small to
+    // fill the pairs with quarters - a shorter serial chain per CTA at the price of one carry row per 8)
+    p.pool_rows = p.H / 4;
+    if (e->small_tiles && e->max_batch * 4 < e->num_sms / 2 && p.H % 8 == 0) p.pool_rows = 8;
+    p.pool_split = p.H / p.pool_rows;
     span = 3 * p.Wp + 128;
     pool_smem = kPoolXchBytes;
   }
@@ -518,7 +531,7 @@ int run_conv(flope_engine* e, ConvLayer& L, int n, cudaStream_t st) {
   const int TM = L.mt * 128 * (L.pair ? 2 : 1);            // positions per (pair) tile
   p.n_n_tiles = L.cout / L.n_tile;
   // work items: (pair) tiles, or for the pooled stem quarter-crops (two per pair)
-  p.n_work = L.pool ? n * kPoolSplit / (L.pair ? 2 : 1) : (p.n_positions + TM - 1) / TM * p.n_n_tiles;
+  p.n_work = L.pool ? (n * p.pool_split + (L.pair ? 1 : 0)) / (L.pair ? 2 : 1) : (p.n_positions + TM - 1) / TM * p.n_n_tiles;
   const int tiles = p.n_work;
   dim3 grid((unsigned)(L.pair ? 2 * std::min(tiles, e->num_sms / 2) : std::min(tiles, e->num_sms)));
   cudaError_t ce = cudaSuccess;
@@ -1008,8 +1021,8 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
     return FLOPE_OK;
   }
   if (!std::strcmp(key, "pdl")) { e->use_pdl = value != 0; drop_graphs(e); return FLOPE_OK; }
-  if (!std::strcmp(key, "pair")) {             // re-plans every layer; the packed weights depend on it, so they must be reloaded
-    e->use_pair = value != 0;
+  if (!std::strcmp(key, "pair") || !std::strcmp(key, "small_tiles")) {   // re-plans every layer; the packed weights depend on it: reload them
+    if (key[0] == 'p') e->use_pair = value != 0; else e->small_tiles = value != 0;
     drop_graphs(e);
     e->weights_loaded = false;
     for (ConvLayer& L : e->layers) { int rc = plan_conv(e, L); if (rc) return rc; }
