@@ -98,6 +98,27 @@ def test_pair_and_single_cta_kernels_agree_bitwise(cuda_lib, net):
         e.close()
 
 
+@pytest.mark.parametrize("size,batch,max_batch", [(32, 5, 5), (64, 37, 37), (96, 9, 64), (160, 3, 3), (192, 12, 300), (256, 2, 2),
+                                                  (288, 3, 3), (224, 1, 1), (224, 70, 70)])
+def test_other_crop_sides_and_batch_sizes(cuda_lib, net, size, batch, max_batch):
+    """PoseResNet is size-agnostic (AdaptiveAvgPool2d, posenet.py:12); the engine takes any multiple of 32.  Sweeps the
+    geometry-dependent code: fused stem bands of 4 / 8 / H/4 rows, the two-kernel stem above 252 px, latency tiles for
+    small max_batch and throughput tiles for large, ragged last tiles."""
+    x = synth.mixed_crops(batch, size, seed=7 + size)
+    want = onet.forward_fp32(net, x)
+    e = cuda_lib.Engine(0, max_batch=max_batch, crop_hw=size)
+    try:
+        e.load_state_dict(net.state_dict())
+        got = e.posenet_forward(x.cuda())
+        torch.cuda.synchronize()
+        assert _rel(got.cpu(), want) < 2e-2
+        again = e.posenet_forward(x.cuda().flip(0)).flip(0)                  # batch order must not matter
+        torch.cuda.synchronize()
+        assert torch.equal(again, got)
+    finally:
+        e.close()
+
+
 def test_orientation_within_half_degree_mean(eng224, net):
     x = synth.mixed_crops(32, 224)
     want = orot.procrustes_to_rotmat(onet.forward_fp32(net, x)).numpy()
