@@ -185,6 +185,28 @@ def workload_config(args):
                            f"{getattr(args, 'inflight', 1)} independent steps in flight per GPU (one engine + stream each)"}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Restrict this process to the CPUs NVML reports as local to its GPU, so that the pinned staging buffers of the
+    end-to-end legs are allocated on that socket (with 8 ranks the H2D copies otherwise cross the socket interconnect).
+    Returns the number of CPUs bound to, or None when NVML / the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -201,6 +223,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    numa = bind_to_gpu_numa_node(local)                 # pinned host buffers are first-touched on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, S, K, W = args.batch, args.size, args.steps, args.warmup
@@ -451,7 +474,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks,
-            "steps_in_flight": len(pool),
+            "steps_in_flight": len(pool), "host_cpus_bound": numa,
             "value_single_stream": world * B * K / (ms_serial / 1e3), "ms_per_step_single_stream": ms_serial / K,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_fr,
                     "crops_per_step": int(nb),
