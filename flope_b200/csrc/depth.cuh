@@ -69,23 +69,31 @@ __global__ void __launch_bounds__(256) erode_valid_kernel(const __grid_constant_
   }
 }
 
-// One CTA per box: masked sum of depth in millimetres (float32 multiply like the reference, fp64 accumulation)
-// and the pixel count.  val = float32(mean) / 1000 in metres (0 when no pixel), count decides reliability.
+// kBoxSplit CTAs per box (row stripes): masked sum of depth in millimetres (float32 multiply like the reference) and
+// the pixel count.  The sum is accumulated as a 64-bit fixed-point integer in units of 2^-20 mm (exact for every float32
+// value of 8 mm and more, rounded to 1e-6 mm below; 2 M pixels x 2^32 stay far below 2^63), so the atomics across
+// CTAs are order-independent and the result is deterministic; box_depth_finish_kernel turns (sum, count) into metres.
+constexpr int kBoxSplit = 16;
+constexpr int kDepthFixShift = 20;
+
 __global__ void __launch_bounds__(256) box_depth_kernel(const __grid_constant__ DepthParams p, const int32_t* __restrict__ boxes,
-                                                        int n, double* __restrict__ val, int32_t* __restrict__ count) {
-  __shared__ double s_sum[8];
+                                                        unsigned long long* __restrict__ acc /* n x 2: sum, count */) {
+  __shared__ unsigned long long s_sum[8];
   __shared__ int s_cnt[8];
   const int b = blockIdx.x;
   const int wmin = max(boxes[4 * b], 0), hmin = max(boxes[4 * b + 1], 0);
   const int wmax = min(boxes[4 * b + 2], p.W), hmax = min(boxes[4 * b + 3], p.H);
   const int bw = max(wmax - wmin, 0), bh = max(hmax - hmin, 0);
-  double sum = 0.0;
+  const int rows = (bh + kBoxSplit - 1) / kBoxSplit;                 // this CTA's stripe of box rows
+  const int r0 = blockIdx.y * rows, r1 = min(bh, r0 + rows);
+  unsigned long long sum = 0;
   int cnt = 0;
-  for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) {
-    const int y = i / bw, x = i - y * bw;
+  for (int i = threadIdx.x; i < bw * max(r1 - r0, 0); i += blockDim.x) {
+    const int y = r0 + i / bw, x = i % bw;
     const long long g = (long long)(hmin + y) * p.W + wmin + x;
     if (p.eroded[g]) {
-      sum += (double)__fmul_rn(depth_metres(p, g), 1000.0f);
+      const float mm = __fmul_rn(depth_metres(p, g), 1000.0f);
+      sum += (unsigned long long)__double2ll_rn((double)mm * (double)(1 << kDepthFixShift));
       ++cnt;
     }
   }
@@ -96,12 +104,25 @@ __global__ void __launch_bounds__(256) box_depth_kernel(const __grid_constant__ 
   if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_cnt[threadIdx.x >> 5] = cnt; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double ts = 0.0;
+    unsigned long long ts = 0;
     int tc = 0;
     for (int w = 0; w < 8; ++w) { ts += s_sum[w]; tc += s_cnt[w]; }
-    count[b] = tc;
-    val[b] = tc ? (double)__fdiv_rn((float)(ts / (double)tc), 1000.0f) : 0.0;
+    if (tc) {
+      atomicAdd(&acc[2 * b], ts);
+      atomicAdd(&acc[2 * b + 1], (unsigned long long)tc);
+    }
   }
+}
+
+// val = float32(mean in mm) / 1000 in metres (0 when no pixel), count decides reliability (>= 50 in the reference)
+__global__ void box_depth_finish_kernel(const unsigned long long* __restrict__ acc, int n, double* __restrict__ val,
+                                        int32_t* __restrict__ count) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const unsigned long long s = acc[2 * b], c = acc[2 * b + 1];
+  count[b] = (int32_t)c;
+  const double mean_mm = c ? ((double)s / (double)(1 << kDepthFixShift)) / (double)c : 0.0;
+  val[b] = c ? (double)__fdiv_rn((float)mean_mm, 1000.0f) : 0.0;
 }
 
 }  // namespace flope

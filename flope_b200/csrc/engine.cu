@@ -937,7 +937,15 @@ int flope_depth_values(int device, const void* d_depth, int depth_dtype, float d
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((W + kErodeTileW - 1) / kErodeTileW, (H + kErodeTileH - 1) / kErodeTileH);
   erode_valid_kernel<<<grid, 256, 0, st>>>(dp);
-  if (n > 0) box_depth_kernel<<<n, 256, 0, st>>>(dp, d_boxes, n, d_val, d_count);
+  if (n > 0) {
+    // (sum, count) accumulators of the row-stripe CTAs: n x 16 bytes from the stream-ordered pool
+    unsigned long long* acc = nullptr;
+    CUDA_TRY(cudaMallocAsync(&acc, (size_t)n * 2 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)n * 2 * sizeof(unsigned long long), st));
+    box_depth_kernel<<<dim3(n, kBoxSplit), 256, 0, st>>>(dp, d_boxes, acc);
+    box_depth_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(acc, n, d_val, d_count);
+    CUDA_TRY(cudaFreeAsync(acc, st));
+  }
   CUDA_TRY(cudaGetLastError());
   return FLOPE_OK;
 }
