@@ -105,7 +105,7 @@ __device__ __forceinline__ float normalise_u8(int img, int mask) {
 //   ((b*(S>>4))>>16) == mulhi(b<<16, S>>4).   The result never leaves [0,255], so no saturation is needed.
 // ---------------------------------------------------------------------------------------------
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(256) roi_bilinear_kernel(const __grid_constant__ RoiParams p) {
+__global__ void __launch_bounds__(256, 4) roi_bilinear_kernel(const __grid_constant__ RoiParams p) {
   // thread = two adjacent output columns (2q, 2q+1) marching down the strip: one thread produces both
   // 16-byte halves of a space-to-depth stem pixel, and the row bookkeeping / coefficient fetches are
   // shared by the two columns.
