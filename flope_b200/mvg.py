@@ -6,6 +6,8 @@ Same names, argument meaning and return types as the reference:
   filter_very_large_bb   sunflower/utils/mvg.py:354-362
   nullify_yaw_batch      sunflower/utils/mvg.py:240-251
   get_points3d           sunflower/utils/mvg.py:387-408   (host, float64: four flops per flower)
+  pose_cam_to_world      sunflower/utils/mvg.py:416-422
+  rot_average            sunflower/utils/mvg.py:365-384   (pairwise SLERP, used by the aggregator)
 ``squarify_filter_batch`` is the vectorised form used by the predictors; it calls
 the C-ABI ``flope_squarify_filter`` (integer, bit-exact with the scalar pair).
 """
@@ -76,3 +78,18 @@ def get_points3d(uv, Zray, K):
     xnyn1_norm = np.linalg.norm(xnyn1, axis=1)
     Z = np.asarray(Zray) / xnyn1_norm
     return xnyn1 * Z.reshape(-1, 1)
+
+
+def pose_cam_to_world(obj_pose, cam_pose):
+    """(N,4,4) object poses in the camera frame, (4,4) camera pose -> (N,4,4) in the world frame."""
+    return cam_pose @ obj_pose
+
+
+def rot_average(quat1, quat2, weight1, weight2):
+    """Row-wise weighted average of two sets of xyzw quaternions by spherical interpolation at t = w2 / (w1 + w2)."""
+    from scipy.spatial.transform import Rotation as R, Slerp
+    avg_quat = []
+    for q1, q2, w1, w2 in zip(quat1, quat2, weight1, weight2):
+        slerp = Slerp([0, 1], R.concatenate([R.from_quat(q1), R.from_quat(q2)]))
+        avg_quat.append(slerp([w2 / (w1 + w2)]).as_quat()[0])
+    return np.array(avg_quat)

@@ -163,6 +163,38 @@ def main():
         yout[f"bbox_{tag}"] = bbox
         yout[f"mask_{tag}"] = mask
     np.savez_compressed(os.path.join(HERE, "yolo_post.npz"), **yout)
+    # ---- aggregation: the reference's own Env3D (scripts/flower_pose_aggregrator.py:23-135) and rot_average
+    #      (mvg.py:365-384) on a seeded sequence of noisy re-observations of 12 flowers ----
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_aggregator", "/root/reference/scripts/flower_pose_aggregrator.py")
+    ref_agg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_agg)
+    arng = np.random.default_rng(55)
+    true_t = arng.uniform(-0.5, 0.5, (12, 3))
+    true_q = sciR.random(12, random_state=8).as_quat()
+    env = ref_agg.Env3D(th=40, score_th=3)
+    frames_t, frames_q = [], []
+    for f in range(14):
+        seen = arng.random(12) < 0.7
+        seen[arng.integers(0, 12)] = True
+        t = true_t[seen] + arng.normal(0, 0.004, (int(seen.sum()), 3))
+        q = (sciR.from_quat(true_q[seen]) * sciR.from_rotvec(arng.normal(0, 0.05, (int(seen.sum()), 3)))).as_quat()
+        if f == 5:                                          # a frame of only-new flowers far away: the no-match branch
+            t, q = t + 3.0, q
+        order = arng.permutation(t.shape[0])
+        frames_t.append(t[order]); frames_q.append(q[order])
+        env.add_measurement(frames_t[-1].copy(), frames_q[-1].copy())
+    fin_t, fin_q = env.get_final_data()
+    aout = {"n_frames": np.array(14), "trans": env.trans, "quat": env.quat, "score": env.score, "final_trans": fin_t,
+            "final_quat": fin_q}
+    for f in range(14):
+        aout[f"t{f}"] = frames_t[f]; aout[f"q{f}"] = frames_q[f]
+    q1, q2 = sciR.random(20, random_state=1).as_quat(), sciR.random(20, random_state=2).as_quat()
+    w1, w2 = arng.uniform(0.1, 5, 20), arng.uniform(0.1, 5, 20)
+    aout.update(ra_q1=q1, ra_q2=q2, ra_w1=w1, ra_w2=w2, ra_out=ref_mvg.rot_average(q1, q2, w1, w2))
+    det = np.hstack([arng.integers(0, 600, (7, 4)).astype(np.float64), arng.uniform(0, 600, (7, 2)), arng.normal(0, 1, (7, 9))])
+    aout["det_rows"] = det
+    np.savez_compressed(os.path.join(HERE, "aggregate.npz"), **aout)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

@@ -1,0 +1,54 @@
+"""Detection-file reader and multi-frame aggregator (flope_b200/aggregate.py) against the outputs of the
+reference's own Env3D / rot_average (tests/golden/aggregate.npz, made from scripts/flower_pose_aggregrator.py and
+sunflower/utils/mvg.py by tests/golden/make_golden.py).  Host-side float64: bit-identical results are required."""
+import os
+
+import numpy as np
+import pytest
+
+from flope_b200 import aggregate as agg
+from flope_b200 import mvg
+from flope_b200.predictor import write_detection_txt
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "aggregate.npz"))
+
+
+def test_env3d_matches_reference_sequence(g):
+    env = agg.Env3D(th=40, score_th=3)
+    for f in range(int(g["n_frames"])):
+        env.add_measurement(g[f"t{f}"].copy(), g[f"q{f}"].copy())
+    assert np.array_equal(env.score, g["score"])
+    assert np.array_equal(env.trans, g["trans"])
+    assert np.array_equal(env.quat, g["quat"])
+    t, q = env.get_final_data()
+    assert np.array_equal(t, g["final_trans"]) and np.array_equal(q, g["final_quat"])
+    assert 0 < t.shape[0] < env.trans.shape[0]                 # the score threshold dropped the one-off detections
+
+
+def test_rot_average_matches_reference(g):
+    assert np.array_equal(mvg.rot_average(g["ra_q1"], g["ra_q2"], g["ra_w1"], g["ra_w2"]), g["ra_out"])
+
+
+def test_detection_txt_round_trip(tmp_path, g):
+    rows = g["det_rows"]
+    p = tmp_path / "000123.txt"
+    write_detection_txt(str(p), rows[:, :4].astype(np.int16), rows[:, 6:].reshape(-1, 3, 3))
+    bbox, uv, rot = agg.read_detection_txt(str(p))
+    assert bbox.dtype == np.int16 and np.array_equal(bbox, rows[:, :4].astype(np.int16))
+    b = rows[:, :4].astype(np.int16).astype(np.float64)
+    assert np.allclose(uv, np.stack([(b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2], 1))
+    assert np.allclose(rot, rows[:, 6:], atol=5e-8)            # '%.7f' rows
+    one = tmp_path / "one.txt"
+    write_detection_txt(str(one), rows[:1, :4].astype(np.int16), rows[:1, 6:].reshape(-1, 3, 3))
+    assert agg.read_detection_txt(str(one))[0].shape == (1, 4)  # a single row still reads as (1,15)
+
+
+def test_pose_helpers(g):
+    tr = np.hstack([np.arange(6, dtype=np.float64).reshape(2, 3), np.tile(np.eye(3).reshape(1, 9), (2, 1))])
+    P = agg.get_pose_mat(tr)
+    assert P.shape == (2, 4, 4) and np.array_equal(P[1, :3, 3], [3, 4, 5]) and np.array_equal(P[0, 3], [0, 0, 0, 1])
+    cam = np.eye(4); cam[:3, 3] = [1, 2, 3]
+    assert np.array_equal(mvg.pose_cam_to_world(P, cam)[:, :3, 3], tr[:, :3] + [1, 2, 3])

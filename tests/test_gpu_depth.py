@@ -149,3 +149,28 @@ def test_fast_predictor_with_raw_yolo_results(cuda_lib, golden_dir, g):
         assert Rt.shape == want["Rt"].shape
         np.testing.assert_allclose(Rt[:, :3, 3], want["Rt"][:, :3, 3], rtol=RTOL, atol=1e-12)
         assert orot.geodesic_deg(Rt[:, :3, :3], want["Rt"][:, :3, :3]).mean() <= 0.5
+
+
+def test_frame_measurements_for_the_aggregator(cuda_lib, g, tmp_path):
+    """aggregate.frame_measurements (detection file + depth + mask + camera pose -> world-frame measurements,
+    scripts/flower_pose_aggregrator.py:189-232) against the same composition on the oracle's depth branch."""
+    from scipy.spatial.transform import Rotation as sciR
+    from flope_b200 import aggregate as agg
+    from flope_b200.predictor import write_detection_txt
+    rng = np.random.default_rng(3)
+    boxes = g["boxes"][[0, 1, 2, 3, 5, 7]]
+    rots = sciR.random(len(boxes), random_state=4).as_matrix()
+    p = tmp_path / "f.txt"
+    write_detection_txt(str(p), boxes, rots)
+    depth_m = g["raw"].astype(np.float32) / 10000.0
+    cam = np.eye(4); cam[:3, :3] = sciR.random(1, random_state=6).as_matrix()[0]; cam[:3, 3] = rng.normal(0, 1, 3)
+    got = agg.frame_measurements(str(p), depth_m, g["mask"], cam, g["K"], None, 0.1, 2.5)
+    bbox, uv, rotmat = agg.read_detection_txt(str(p))
+    val, rel = od.get_depth_value(bbox, depth_m, g["mask"], near_plane=0.1, far_plane=2.5)
+    xyz = od.get_points3d(uv[rel], np.asarray(val)[rel], g["K"])
+    want_t = (cam[:3, :3] @ xyz.T).T + cam[:3, 3]
+    want_R = cam[:3, :3] @ rotmat[rel].reshape(-1, 3, 3)
+    assert got is not None and got[0].shape == want_t.shape and rel.sum() < len(boxes)
+    np.testing.assert_allclose(got[0], want_t, rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(sciR.from_quat(got[1]).as_matrix(), want_R, atol=1e-6)
+    assert agg.frame_measurements(str(p), depth_m, np.zeros_like(g["mask"]), cam, g["K"]) is None
