@@ -139,12 +139,20 @@ int flope_engine_profile_read(flope_engine* e, char* names, int names_len, float
 
 /* ---- test / bring-up hooks (used only by tests/) ---- */
 /* Copy a named intermediate activation of the last forward as (n,C,H,W) float32 into d_out.
- * Names: "stem", "maxpool", "layer1.0" ... "layer4.1".  Returns C*H*W, or a negative error. */
+ * Names: "stem" (only written by the two-kernel stem path), "maxpool", "layer1.0" ... "layer4.1".
+ * Returns C*H*W, or a negative error. */
 int64_t flope_debug_activation(flope_engine* e, const char* name, int n, float* d_out, void* stream);
 /* Evaluate the device mask/normalise arithmetic for all (mask,img) uint8 pairs: d_out (256,256) f32. */
 int flope_debug_normalise_lut(float* d_out, void* stream);
-/* Set a named option: "use_graph" = 0/1 (replay the backbone as a CUDA graph; default 1);
- * "fuse_pool" = 0/1 (stem conv + max-pool as one kernel instead of two; default 0, crop side <= 252). */
+/* Set a named option (A/B switches for tests and tools; the defaults are the product configuration):
+ *   "use_graph"   0/1  replay the backbone as a CUDA graph (default 1)
+ *   "pdl"         0/1  programmatic dependent launch between the backbone kernels (default 1)
+ *   "fuse_pool"   0/1  stem conv + max-pool as one kernel instead of two (default 1 when the crop side is <= 252)
+ *   "roi_strip"   even 2..128  output rows per CTA of the bilinear ROI kernel (default 14)
+ *   "pair"        0/1  CTA-pair (tcgen05 cta_group::2) conv kernels instead of single-CTA ones (default 1)
+ *   "small_tiles" 0/1  latency-oriented tiles when max_batch cannot fill the SMs (default 1)
+ * "pair" and "small_tiles" change the packed-weight layout: call flope_engine_load_weights again afterwards.
+ * Activation names for flope_debug_activation additionally include "x0" (the stem's space-to-depth input). */
 int flope_debug_set(flope_engine* e, const char* key, int value);
 
 #ifdef __cplusplus
