@@ -110,8 +110,8 @@ int flope_infer_frames(flope_engine* e, const uint8_t* d_frames, int n_frames, i
  *   d_scratch    (H,W) uint8 work buffer (receives the eroded validity mask)
  *   d_val        (n) float64: mean depth in metres over the box's valid pixels (0 when there is none)
  *   d_count      (n) int32: number of valid pixels; the reference calls a box reliable when count >= 50
- * Validity, erosion and counts are exact; the mean is accumulated in fp64 where numpy sums fp32 pairwise
- * (agreement ~1e-7 relative). */
+ * Validity, erosion and counts are exact; the sum is accumulated exactly (64-bit fixed point, order-independent)
+ * where numpy sums float32 pairwise: agreement ~1e-7 relative, results deterministic. */
 int flope_depth_values(int device, const void* d_depth, int depth_dtype, float depth_div, const uint8_t* d_mask, int H, int W,
                        const int32_t* d_boxes, int n, float near_plane, float far_plane, int erode_k, uint8_t* d_scratch,
                        double* d_val, int32_t* d_count, void* stream);
