@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -83,7 +84,6 @@ struct ConvLayer {
   std::vector<std::vector<TapDef>> group_taps;   // per group: (r,s) of each weight tile, for packing
   std::vector<int> group_cin;                    // first input channel of each group
   __nv_bfloat16* d_w = nullptr;
-  float* d_scale = nullptr;
   float* d_bias = nullptr;
 };
 
@@ -553,12 +553,12 @@ int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
   size_t li = 0;
   // mode 2: the stem .. layer4 conv_igemm launches as they run in production (back to back, programmatic
   // dependent launch overlapping each prologue with its predecessor's tail) between ONE pair of events
-  ProfScope* chain = new ProfScope(e, "conv_chain", st, 2);
+  std::unique_ptr<ProfScope> chain(new ProfScope(e, "conv_chain", st, 2));
   if (e->fuse_pool) {
     ++li;
-    if ((rc = run_conv(e, e->stem_pool, n, st))) { delete chain; return rc; }   // stem conv + BN + ReLU + max-pool in one kernel
+    if ((rc = run_conv(e, e->stem_pool, n, st))) return rc;   // stem conv + BN + ReLU + max-pool in one kernel
   } else {
-    if ((rc = run_conv(e, e->layers[li++], n, st))) { delete chain; return rc; }   // stem
+    if ((rc = run_conv(e, e->layers[li++], n, st))) return rc;   // stem
     const ActBuf& a = e->bufs[e->buf_stem];
     const ActBuf& b = e->bufs[e->buf_mp_out];
     const long long total = (long long)(a.g.C / 8) * n * b.g.H * b.g.W;
@@ -567,8 +567,8 @@ int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
     ++e->launches;
   }
   for (; li + 1 < e->layers.size(); ++li)
-    if ((rc = run_conv(e, e->layers[li], n, st))) { delete chain; return rc; }
-  delete chain;
+    if ((rc = run_conv(e, e->layers[li], n, st))) return rc;
+  chain.reset();
   {
     const ActBuf& a = e->bufs[e->buf_pool_in];
     const ActBuf& b = e->bufs[e->buf_pool];
@@ -719,8 +719,8 @@ void flope_engine_destroy(flope_engine* e) {
   drop_graphs(e);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (ActBuf& b : e->bufs) cudaFree(b.d);
-  for (ConvLayer& L : e->layers) { cudaFree(L.d_w); cudaFree(L.d_scale); cudaFree(L.d_bias); }
-  cudaFree(e->stem_pool.d_w); cudaFree(e->stem_pool.d_scale); cudaFree(e->stem_pool.d_bias);
+  for (ConvLayer& L : e->layers) { cudaFree(L.d_w); cudaFree(L.d_bias); }
+  cudaFree(e->stem_pool.d_w); cudaFree(e->stem_pool.d_bias);
   cudaFree(e->d_feat); cudaFree(e->d_wrot); cudaFree(e->d_brot); cudaFree(e->d_r9);
   delete e;
 }
@@ -786,13 +786,11 @@ int flope_engine_load_weights(flope_engine* e, const flope_tensor_desc* tensors,
     }
     std::vector<__nv_bfloat16> packed;
     pack_weights_host(L, w, scale, w2, scale2, packed);
-    cudaFree(L.d_w); cudaFree(L.d_scale); cudaFree(L.d_bias);
-    L.d_w = nullptr; L.d_scale = nullptr; L.d_bias = nullptr;
+    cudaFree(L.d_w); cudaFree(L.d_bias);
+    L.d_w = nullptr; L.d_bias = nullptr;
     CUDA_TRY(cudaMalloc(&L.d_w, packed.size() * sizeof(__nv_bfloat16)));
-    CUDA_TRY(cudaMalloc(&L.d_scale, L.cout * sizeof(float)));
     CUDA_TRY(cudaMalloc(&L.d_bias, L.cout * sizeof(float)));
     CUDA_TRY(cudaMemcpy(L.d_w, packed.data(), packed.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(L.d_scale, scale.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(L.d_bias, bias.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice));
   }
   const float* wr = need("fc_rot.weight", (int64_t)9 * e->feat_dim);
