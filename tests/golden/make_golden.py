@@ -195,6 +195,35 @@ def main():
     det = np.hstack([arng.integers(0, 600, (7, 4)).astype(np.float64), arng.uniform(0, 600, (7, 2)), arng.normal(0, 1, (7, 9))])
     aout["det_rows"] = det
     np.savez_compressed(os.path.join(HERE, "aggregate.npz"), **aout)
+    # ---- tracking: the reference's own FlowerModel.assign_meas_to_state (flower_model.py:146-216) with filterpy's
+    #      KalmanFilter replaced by the restatement in flope_b200/flower_model.py (filterpy is absent here: the filter
+    #      arithmetic itself stays unpinned, the association / update-order / normalisation logic is the reference's) ----
+    from flope_b200 import flower_model as our_fm
+    fk = types.ModuleType("filterpy.kalman")
+    fk.KalmanFilter = our_fm.KalmanFilter
+    sys.modules["filterpy"] = types.ModuleType("filterpy")
+    sys.modules["filterpy.kalman"] = fk
+    sys.modules.pop("sunflower.predictor.flower_model", None)
+    sys.modules["matplotlib.ticker"] = mock.MagicMock()
+    sys.modules["icecream"] = types.SimpleNamespace(ic=lambda *a, **k: None)
+    from sunflower.predictor import flower_model as ref_fm
+    ref_fm.ic = lambda *a, **k: None
+    fm = object.__new__(ref_fm.FlowerModel)
+    fm.get_plots, fm.state, fm.scores, fm.kfs, fm.th = False, None, None, [], 50 / 1000
+    trng = np.random.default_rng(91)
+    t_true = trng.uniform(-0.4, 0.4, (9, 3))
+    q_true = sciR.random(9, random_state=12).as_quat()
+    tout = {"n_frames": np.array(12)}
+    for f in range(12):
+        seen = trng.random(9) < 0.75
+        seen[trng.integers(0, 9)] = True
+        t = t_true[seen] + trng.normal(0, 0.006, (int(seen.sum()), 3))
+        q = (sciR.from_quat(q_true[seen]) * sciR.from_rotvec(trng.normal(0, 0.04, (int(seen.sum()), 3)))).as_quat()
+        meas = np.hstack([t, q])[trng.permutation(int(seen.sum()))]
+        tout[f"m{f}"] = meas
+        fm.assign_meas_to_state(meas.copy())
+    tout.update(state=fm.state, scores=fm.scores, kf_x=np.array([k.x for k in fm.kfs]), kf_P=np.array([k.P for k in fm.kfs]))
+    np.savez_compressed(os.path.join(HERE, "tracking.npz"), **tout)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

@@ -174,3 +174,33 @@ def test_frame_measurements_for_the_aggregator(cuda_lib, g, tmp_path):
     np.testing.assert_allclose(got[0], want_t, rtol=RTOL, atol=1e-9)
     np.testing.assert_allclose(sciR.from_quat(got[1]).as_matrix(), want_R, atol=1e-6)
     assert agg.frame_measurements(str(p), depth_m, np.zeros_like(g["mask"]), cam, g["K"]) is None
+
+
+def test_flower_model_add_data_end_to_end(cuda_lib, g):
+    """FlowerModel.add_data (flower_model.py:219-255) on the GPU predictor: camera-frame poses, world-frame poses and
+    the tracker state after two frames of the same scene."""
+    from scipy.spatial.transform import Rotation as sciR
+    from flope_b200 import predictor as P, synth
+    from flope_b200.flower_model import FlowerModel
+    from flope_b200.posenet import PoseResNet
+    from oracle import posenet as onet, resize as ores
+    net = onet.build(synth.WEIGHT_SEED)
+    m = PoseResNet(device="cuda:0", max_batch=8, crop_hw=224)
+    m.load_state_dict(net.state_dict())
+    det = g["boxes"][[0, 1, 2, 3, 7]].astype(np.int16)
+    pp = P.PosePredictor("cuda:0", detector=lambda rgb: (det, g["mask"]), posenet=m, crop_hw=224, interp=ores.BILINEAR, K=g["K"])
+    fm = FlowerModel(dist_th=50, pose_predictor=pp)
+    frame = np.random.default_rng(12).integers(0, 256, (360, 640, 3), dtype=np.uint8)
+    cam = np.concatenate([[0.1, -0.2, 0.3], sciR.from_euler("xyz", [10, 20, 30], degrees=True).as_quat()])
+    cam_pose, world_pose = fm.add_data(frame, g["raw"], cam, ignore=True)
+    assert cam_pose.dtype == np.float64 and world_pose.dtype == np.float32 and cam_pose.shape == world_pose.shape
+    Rc = sciR.from_quat(cam[3:]).as_matrix()
+    np.testing.assert_allclose(world_pose[:, :3, 3], (Rc @ cam_pose[:, :3, 3].T).T + cam[:3], atol=1e-6)
+    n = cam_pose.shape[0]
+    assert fm.get_state().shape == (n, 7) and np.array_equal(fm.scores, np.ones(n))
+    fm.add_data(frame, g["raw"], cam, ignore=True)                 # same scene again: every flower re-identified
+    assert fm.get_state().shape == (n, 7) and np.array_equal(fm.scores, 2 * np.ones(n))
+    np.testing.assert_allclose(fm.get_filtered_state()[:, :3], fm.get_state()[:, :3], atol=1e-9)
+    empty = FlowerModel(pose_predictor=P.PosePredictor("cuda:0", detector=lambda rgb: (np.zeros((0, 4), np.int16), g["mask"]),
+                                                       posenet=m, crop_hw=224, K=g["K"]))
+    assert empty.add_data(frame, g["raw"], cam) == (None, None)
