@@ -76,3 +76,25 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "/root/reference" not in src, f
+
+
+def test_squarify_filter_property_vs_reference_arithmetic(L):
+    """Random boxes far outside the golden set (negative coordinates, degenerate and inverted boxes, frame edges): the C
+    ABI host function must agree with the reference's scalar arithmetic (true division + int() truncation, restated in
+    flope_b200/mvg.py and pinned by the golden test above) on every one of them."""
+    from hypothesis import given, settings, strategies as st
+    from flope_b200 import mvg
+
+    coord = st.integers(min_value=-5000, max_value=5000)
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.tuples(coord, coord, coord, coord), min_size=1, max_size=40), st.integers(1, 4000), st.integers(1, 4000))
+    def check(boxes, H, W):
+        b = np.array(boxes, dtype=np.int32)
+        sq, keep = _lib.squarify_filter(b, H, W)
+        want = np.array([mvg.squarify_bb([int(v) for v in bb]) for bb in b], dtype=np.int64).reshape(-1, 4)
+        want_keep = np.array([mvg.bb_in_frame(s, (H, W, 3)) for s in want], dtype=bool)
+        assert np.array_equal(keep, want_keep)
+        assert np.array_equal(sq, want[want_keep].astype(np.int32))
+
+    check()
