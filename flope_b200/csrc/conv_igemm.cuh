@@ -100,7 +100,39 @@ struct ConvParams {
   long long in2_plane;
   int in2_base;
   int first_group2;            // == n_groups when there is no second source
+  int res_layer;               // chain index of the layer that writes `res` inside this launch, or -1
 };
+
+// A chain = up to four layers of one ResNet stage (same position space, same tile configuration) in ONE persistent
+// launch.  Work items are ordered layer-major, (layer l, tile t) = l * n_work + t, and dealt round-robin as before, so
+// the CTAs that finish layer l's last partial wave start on layer l+1 at once.  Tile (l, t) reads the outputs of tiles
+// (l-1, t-1 .. t+1) (its halo never reaches further) - and, being the only reader of those ranges in layer l-1's
+// input buffer, may also overwrite that buffer's tile t once they are done; every finished tile publishes itself in
+// `flags` (a counter per position tile: n_n_tiles x CTAs of a pair parts), consumers wait on the three counters.
+constexpr int kMaxChain = 4;
+struct ConvChain {
+  ConvParams L[kMaxChain];
+  int n_layers;
+  int n_m_tiles;               // position tiles per layer
+  uint32_t* flags;             // [n_layers][n_m_tiles] completion counters, zeroed before the launch (nullptr: single layer)
+  uint32_t expected;           // counter value of a finished position tile
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded spin until the counter reaches `expected` (a dependency bug must trap, never hang the box).
+__device__ __forceinline__ void wait_tile_flag(const uint32_t* flag, uint32_t expected) {
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(flag) < expected) {
+    if (++spins > (1u << 22)) {
+      printf("flope: tile-flag timeout block=%d thread=%d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 
 __host__ __device__ constexpr int pow2_at_least(int v) { int r = 32; while (r < v) r <<= 1; return r; }
 
@@ -116,7 +148,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 template <int N_TILE, int MT, int KP, bool POOL, bool PAIR, int TAPS>
-__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvChain ch) {
+  const ConvParams& p = ch.L[0];             // everything the layers of a chain share: geometry, tile counts, ring sizes, halo
   static_assert(!POOL || (N_TILE == 64 && MT == 4), "the pooled stem uses four conv rows x 64 channels per tile");
   constexpr int TM = MT * 128;
   constexpr int NB_ROWS = PAIR ? N_TILE / 2 : N_TILE;            // weight rows this CTA holds per tile
@@ -145,7 +178,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   const uint32_t a_slot_bytes = a_plane_bytes * KC8;
   constexpr uint32_t b_tile_bytes = (uint32_t)KC8 * NB_ROWS * 16u;
   uint8_t* a_ring = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 512 + (size_t)p.Cout * sizeof(float) + 127) & ~uintptr_t(127));
+      (reinterpret_cast<uintptr_t>(smem_raw) + 512 + (size_t)ch.n_layers * p.Cout * sizeof(float) + 127) & ~uintptr_t(127));
   uint8_t* b_ring = a_ring + (size_t)p.n_a_slots * a_slot_bytes;
   // POOL: lane-31 hand-over between the four lane-quarter warps of a channel slice: [parity][slice][quarter][2 rows][8]
   uint32_t* pool_xch = reinterpret_cast<uint32_t*>(b_ring + (size_t)p.n_b_slots * b_tile_bytes);
@@ -158,6 +191,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   const int first_work = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // work is dealt to pairs (or CTAs) round-robin
   const int work_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int tiles_per_work = POOL ? (p.pool_rows >> 2) + 1 : 1; // POOL: one carry tile + pool_rows/4 four-row tiles
+  const int total_work = ch.n_layers * p.n_work;                 // layer-major work items of the chain
 
   // First position of this CTA's part of tile `tt` of work item `w`.
   //   plain: tile w / n_n_tiles covers TILE_POS consecutive positions; CTA r of a pair takes the r-th half
@@ -180,7 +214,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     if (PAIR) { tmem_alloc2(tmem_ptr, TMEM_COLS); tmem_relinquish2(); }
     else { tmem_alloc(tmem_ptr, TMEM_COLS); tmem_relinquish(); }
   }
-  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias[i];
+  for (int l = 0; l < ch.n_layers; ++l)
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[l * p.Cout + i] = ch.L[l].bias[i];
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast commit
@@ -199,25 +234,36 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     int a_slot = 0, b_slot = 0;
     uint32_t a_phase = 0, b_phase = 0;
     bool first = true;
-    for (int w = first_work; w < p.n_work; w += work_stride) {
+    for (int gw = first_work; gw < total_work; gw += work_stride) {
+      const int l = gw / p.n_work, w = gw - l * p.n_work;
+      const ConvParams& q = ch.L[l];
+      if (l > 0) {
+        // the producing layer's tiles under this tile's halo must be complete (and visible to the TMA unit)
+        const int m = w / p.n_n_tiles;
+        const uint32_t* fl = ch.flags + (size_t)(l - 1) * ch.n_m_tiles;
+        if (m > 0) wait_tile_flag(fl + m - 1, ch.expected);
+        wait_tile_flag(fl + m, ch.expected);
+        if (m + 1 < ch.n_m_tiles) wait_tile_flag(fl + m + 1, ch.expected);
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
       for (int tt = 0; tt < tiles_per_work; ++tt) {
         const int n_tile = POOL ? 0 : w % p.n_n_tiles;
         const int tile_start = tile_first_pos(w, tt);
         // PAIR: weights are packed [n_tile][tile][rank][k8][N_TILE/2][8], so each CTA's half is one contiguous copy
-        const __nv_bfloat16* wtile = p.wgt + ((size_t)n_tile * p.taps_total * (PAIR ? 2 : 1) + rank) * (b_tile_bytes / 2);
-        for (int g = 0; g < p.n_groups; ++g) {
+        const __nv_bfloat16* wtile = q.wgt + ((size_t)n_tile * q.taps_total * (PAIR ? 2 : 1) + rank) * (b_tile_bytes / 2);
+        for (int g = 0; g < q.n_groups; ++g) {
           mbar_wait(&a_empty[a_slot], a_phase ^ 1);
           mbar_expect_tx_if(leader, &a_full[a_slot], a_slot_bytes);
           const uint32_t a_dst = a_ring_addr + a_slot * a_slot_bytes;
-          const bool second = g >= p.first_group2;
-          const long long a_plane = second ? p.in2_plane : p.in_plane;
-          const __nv_bfloat16* src = (second ? p.in2 : p.in) +
-              ((long long)p.group_plane[g] * a_plane + (second ? p.in2_base : p.in_base) + tile_start - p.halo_before) * 8;
+          const bool second = g >= q.first_group2;
+          const long long a_plane = second ? q.in2_plane : q.in_plane;
+          const __nv_bfloat16* src = (second ? q.in2 : q.in) +
+              ((long long)q.group_plane[g] * a_plane + (second ? q.in2_base : q.in_base) + tile_start - p.halo_before) * 8;
 #pragma unroll
           for (int j = 0; j < KC8; ++j)
             bulk_g2s_if(leader, a_dst + j * a_plane_bytes, src + (long long)j * a_plane * 8, a_plane_bytes, &a_full[a_slot]);
           if (++a_slot == p.n_a_slots) { a_slot = 0; a_phase ^= 1; }
-          const int ntaps = p.group_ntaps[g];
+          const int ntaps = q.group_ntaps[g];
           if (!p.b_resident || first) {
             for (int t = 0; t < ntaps; ++t) {
               mbar_wait(&b_empty[b_slot], b_phase ^ 1);
@@ -240,12 +286,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     int a_slot = 0, b_slot = 0;
     uint32_t a_phase = 0, b_phase = 0;
     bool first = true;
-    for (int w = first_work; w < p.n_work; w += work_stride) {
+    for (int gw = first_work; gw < total_work; gw += work_stride) {
+      const ConvParams& q = ch.L[gw / p.n_work];
       for (int tt = 0; tt < tiles_per_work; ++tt) {
-        for (int g = 0; g < p.n_groups; ++g) {
+        for (int g = 0; g < q.n_groups; ++g) {
           mbar_wait(&a_full[a_slot], a_phase);
           mbar_arrive_remote_if(leader, a_full_remote + a_slot * 8);
-          const int ntaps = p.group_ntaps[g];
+          const int ntaps = q.group_ntaps[g];
           for (int t = 0; t < ntaps; ++t) {
             if (!p.b_resident || first) {
               mbar_wait(&b_full[b_slot], b_phase);
@@ -274,7 +321,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     int a_slot = 0, b_slot = 0;
     uint32_t a_phase = 0, b_phase = 0;
     uint32_t it = 0;
-    for (int w = first_work; w < p.n_work; w += work_stride) {
+    for (int gw = first_work; gw < total_work; gw += work_stride) {
+      const ConvParams& q = ch.L[gw / p.n_work];
       for (int tt = 0; tt < tiles_per_work; ++tt, ++it) {
         const uint32_t stage = it & 1;
         // POOL: the carry tile that opens a work item only needs its last row (a warp-uniform branch: the issue
@@ -326,10 +374,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           b_slot += NT;
           if (b_slot == p.n_b_slots) { b_slot = 0; b_phase ^= (p.b_resident ? 0u : 1u); }
         };
-        for (int g = 0; g < p.n_groups; ++g) {
+        for (int g = 0; g < q.n_groups; ++g) {
           mbar_wait(&a_full[a_slot], a_phase);
           const uint32_t a_grp = a_lo0 + a_slot * a_slot_units;
-          const bool last_group = g == p.n_groups - 1;
+          const bool last_group = g == q.n_groups - 1;
           if (TAPS == 16) {
             // stem: 4x4 stride-1 window on the space-to-depth grid, one window row (4 taps, shifts +0..+3) per
             // iteration; all 16 weight tiles are resident (n_b_slots == 16), so b_slot + j never wraps mid-row
@@ -339,10 +387,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
               issue_taps(std::integral_constant<int, 4>{}, a_row, r == 3, last_group);
           } else {
             // per-group tap tables (3x3, stride-2 phases, 1x1, fc)
-            const int tofs = p.group_tapofs[g];
-            const int ntaps = p.group_ntaps[g];
+            const int tofs = q.group_tapofs[g];
+            const int ntaps = q.group_ntaps[g];
             for (int t = 0; t < ntaps; ++t)
-              issue_taps(std::integral_constant<int, 1>{}, a_grp + (uint32_t)p.tap_shift[tofs + t], t == ntaps - 1, last_group);
+              issue_taps(std::integral_constant<int, 1>{}, a_grp + (uint32_t)q.tap_shift[tofs + t], t == ntaps - 1, last_group);
           }
           if (++a_slot == p.n_a_slots) { a_slot = 0; a_phase ^= 1; }
         }
@@ -362,7 +410,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       else if (lane == 0) mbar_arrive(&acc_empty[stage]);
     };
     uint32_t it = 0;
-    for (int w = first_work; w < p.n_work; w += work_stride) {
+    for (int gw = first_work; gw < total_work; gw += work_stride) {
+      const int l = gw / p.n_work, w = gw - l * p.n_work;
+      const ConvParams& q = ch.L[l];
+      const float* bias_l = s_bias + l * p.Cout;
       if constexpr (POOL) {
         // ---------- stem: conv + BN + ReLU rows -> 3x3/s2 max-pool, two pooled rows per four-row tile ----------
         const int unit = PAIR ? 2 * w + (int)rank : w;
@@ -371,7 +422,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const bool col_ok = col < p.W;
         float bias16[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) bias16[j] = s_bias[sub * 16 + j];
+        for (int j = 0; j < 16; ++j) bias16[j] = bias_l[sub * 16 + j];
         uint32_t carry[8];                                    // conv row 4t-1 (post-ReLU bf16x2), 16 channels
 #pragma unroll
         for (int j = 0; j < 8; ++j) carry[j] = 0u;
@@ -447,6 +498,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const int cout_base = n_tile * N_TILE;
         const uint32_t acc = tmem_base + stage * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
         bool waited = false;
+        if (q.res_layer >= 0) {                 // residual written earlier in this launch: its tile must be published
+          wait_tile_flag(ch.flags + (size_t)q.res_layer * ch.n_m_tiles + w / p.n_n_tiles, ch.expected);
+          __syncwarp();
+        }
 #pragma unroll 1
         for (int c = sub; c < MT * NCHUNK; c += NSUB) {
           const int mt = c / NCHUNK;
@@ -459,10 +514,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           const bool valid = pos >= 0 && pos < p.n_positions && h < p.H && ww < p.W;
           const int plane0 = (cout_base + c0) >> 3;
           uint4 res[4];
-          if (p.res != nullptr && valid) {     // issued before the accumulator wait: latency hidden behind the MMAs
-            const __nv_bfloat16* rp = p.res + ((long long)plane0 * p.res_plane + p.res_base + ((long long)n * p.res_Hp + h) * p.res_Wp + ww) * 8;
+          if (q.res != nullptr && valid) {     // issued before the accumulator wait: latency hidden behind the MMAs
+            // (L2 loads: inside a chain the residual may have been written by another SM moments ago)
+            const __nv_bfloat16* rp = q.res + ((long long)plane0 * q.res_plane + q.res_base + ((long long)n * q.res_Hp + h) * q.res_Wp + ww) * 8;
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) res[j8] = __ldg(reinterpret_cast<const uint4*>(rp + (long long)j8 * p.res_plane * 8));
+            for (int j8 = 0; j8 < 4; ++j8) res[j8] = __ldcg(reinterpret_cast<const uint4*>(rp + (long long)j8 * q.res_plane * 8));
           }
           if (!waited) {
             mbar_wait(&acc_full[stage], (it >> 1) & 1);
@@ -477,11 +533,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(s_bias + cout_base + c0 + j);
+              const float4 b = *reinterpret_cast<const float4*>(bias_l + cout_base + c0 + j);
               v[j] = __uint_as_float(v32[j]) + b.x; v[j + 1] = __uint_as_float(v32[j + 1]) + b.y;
               v[j + 2] = __uint_as_float(v32[j + 2]) + b.z; v[j + 3] = __uint_as_float(v32[j + 3]) + b.w;
             }
-            if (p.res != nullptr) {
+            if (q.res != nullptr) {
 #pragma unroll
               for (int j8 = 0; j8 < 4; ++j8) {
                 const uint4 rr = res[j8];
@@ -489,34 +545,34 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                 v[j8 * 8 + 4] += bf16_lo(rr.z); v[j8 * 8 + 5] += bf16_hi(rr.z); v[j8 * 8 + 6] += bf16_lo(rr.w); v[j8 * 8 + 7] += bf16_hi(rr.w);
               }
             }
-            if (p.out_mode == OUT_F32_ROWS) {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)pos * p.Cout + cout_base + c0);
+            if (q.out_mode == OUT_F32_ROWS) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(q.out) + (long long)pos * p.Cout + cout_base + c0);
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                if (p.relu) dst[j >> 2] = make_float4(fmaxf(v[j], 0.f), fmaxf(v[j + 1], 0.f), fmaxf(v[j + 2], 0.f), fmaxf(v[j + 3], 0.f));
+                if (q.relu) dst[j >> 2] = make_float4(fmaxf(v[j], 0.f), fmaxf(v[j + 1], 0.f), fmaxf(v[j + 2], 0.f), fmaxf(v[j + 3], 0.f));
                 else dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
               }
             } else {
               long long out_pix;
               int plane = plane0;
-              if (p.out_mode == OUT_PLAIN) {
-                out_pix = p.out_base + ((long long)n * p.out_Hp + h) * p.out_Wp + ww;
+              if (q.out_mode == OUT_PLAIN) {
+                out_pix = q.out_base + ((long long)n * q.out_Hp + h) * q.out_Wp + ww;
               } else {
-                out_pix = p.out_base + ((long long)n * p.out_Hp + (h >> 1)) * p.out_Wp + (ww >> 1);
+                out_pix = q.out_base + ((long long)n * q.out_Hp + (h >> 1)) * q.out_Wp + (ww >> 1);
                 plane += (((h & 1) << 1) | (ww & 1)) * (p.Cout >> 3);
               }
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)plane * p.out_plane + out_pix) * 8;
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(q.out) + ((long long)plane * q.out_plane + out_pix) * 8;
 #pragma unroll
               for (int j8 = 0; j8 < 4; ++j8) {
                 uint4 o;
-                if (p.relu) {
+                if (q.relu) {
                   o.x = pack_bf16x2_relu(v[j8 * 8 + 0], v[j8 * 8 + 1]); o.y = pack_bf16x2_relu(v[j8 * 8 + 2], v[j8 * 8 + 3]);
                   o.z = pack_bf16x2_relu(v[j8 * 8 + 4], v[j8 * 8 + 5]); o.w = pack_bf16x2_relu(v[j8 * 8 + 6], v[j8 * 8 + 7]);
                 } else {
                   o.x = pack_bf16x2(v[j8 * 8 + 0], v[j8 * 8 + 1]); o.y = pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
                   o.z = pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]); o.w = pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
                 }
-                *reinterpret_cast<uint4*>(dst + (long long)j8 * p.out_plane * 8) = o;
+                *reinterpret_cast<uint4*>(dst + (long long)j8 * q.out_plane * 8) = o;
               }
             }
           }
@@ -525,6 +581,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           // a warp with no chunk in this configuration still takes part in the accumulator hand-back
           mbar_wait(&acc_full[stage], (it >> 1) & 1);
           release_acc(stage);
+        }
+        if (ch.flags != nullptr) {
+          // publish this CTA's part of the tile: every epilogue warp has issued its stores -> barrier -> one thread
+          // fences (cumulative at GPU scope) and bumps the tile's counter
+          asm volatile("bar.sync 5, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          if (threadIdx.x == 64) {
+            __threadfence();
+            atomicAdd(ch.flags + (size_t)l * ch.n_m_tiles + w / p.n_n_tiles, 1u);
+          }
         }
         ++it;
       }

@@ -119,8 +119,8 @@ cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 
 template <int N_TILE, int MT, int KP, bool POOL, bool PAIR, int TAPS>
-cudaError_t conv_launch_t(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st, bool pdl) {
-  return launch_k(conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR, TAPS>, grid, dim3(kConvThreads), smem, st, PAIR ? 2 : 1, pdl, p);
+cudaError_t conv_launch_t(const ConvChain& c, dim3 grid, size_t smem, cudaStream_t st, bool pdl) {
+  return launch_k(conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR, TAPS>, grid, dim3(kConvThreads), smem, st, PAIR ? 2 : 1, pdl, c);
 }
 
 // (N_TILE, MT, KP, POOL, PAIR, TAPS): output channels per tile, 128-pixel sub-tiles per CTA and tile, K=16 MMAs per weight
@@ -141,11 +141,12 @@ cudaError_t conv_set_all_attrs() {
   return cudaSuccess;
 }
 // returns false when no kernel instance matches; *err receives the launch status otherwise
-bool conv_launch(int n_tile, int mt, bool pair, int taps, const ConvParams& p, dim3 grid, size_t smem, cudaStream_t st, bool pdl,
+bool conv_launch(int n_tile, int mt, bool pair, int taps, const ConvChain& c, dim3 grid, size_t smem, cudaStream_t st, bool pdl,
                  cudaError_t* err) {
+  const ConvParams& p = c.L[0];
 #define X(N, M, K, P, R, T)                                                                                        \
   if (n_tile == N && mt == M && p.kc8 == 2 * K && (p.pool_rows > 0) == P && pair == R && taps == T) {              \
-    *err = conv_launch_t<N, M, K, P, R, T>(p, grid, smem, st, pdl);                                                \
+    *err = conv_launch_t<N, M, K, P, R, T>(c, grid, smem, st, pdl);                                                \
     return true;                                                                                                   \
   }
   FOR_EACH_CONV_CFG(X)
@@ -164,6 +165,10 @@ struct flope_engine {
   std::vector<ConvLayer> layers;
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
   int roi_strip = 14;                            // output rows per CTA of the bilinear ROI kernel (even; crops below 448 px)
+  bool use_chain = true;                         // one persistent launch per ResNet stage (four convs) with per-tile completion flags
+  std::vector<std::vector<int>> chains;          // layer indices of each stage
+  uint32_t* d_flags = nullptr;                   // completion counters of all chains, zeroed at the start of every forward
+  size_t flags_per_chain = 0;                    // counters reserved per chain (kMaxChain layers x position tiles at max_batch)
   bool small_tiles = true;                       // latency-oriented tiles when max_batch is too small to fill the SMs
   bool use_pdl = true;                           // programmatic dependent launch between the backbone kernels
   bool use_pair = true;                          // CTA-pair (cta_group::2) conv kernels; flope_debug_set "pair" 0 selects the single-CTA ones
@@ -282,8 +287,8 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
           L.group_taps.push_back(tds[q]);
           L.group_cin.push_back(c * 64);
         }
-      p.halo_before = Wp + 1; p.halo_after = 0;
-      break;
+      p.halo_before = Wp + 1; p.halo_after = Wp + 1;   // halo_after is not needed by these taps: kept equal to the 3x3
+      break;                                          // convs' so that a stage's layers share one ring geometry (chains)
     }
     case K_DOWN1_S2: {
       p.kc8 = 8;
@@ -375,7 +380,7 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
   }
   const int halo = p.halo_before + p.halo_after;
   auto smem_of = [&](int n_a, int n_b) {
-    return (size_t)1024 + (size_t)L.cout * sizeof(float) + (size_t)n_a * p.kc8 * (span + halo) * 16 +
+    return (size_t)1024 + (size_t)kMaxChain * L.cout * sizeof(float) + (size_t)n_a * p.kc8 * (span + halo) * 16 +
            (size_t)n_b * p.kc8 * nb_rows * 16 + pool_smem;
   };
   // weight tiles are consumed every MT*kc8/2 MMAs, so several must be in flight to cover L2 latency;
@@ -443,6 +448,10 @@ int build_network(flope_engine* e) {
     }
     add_conv(e, dn + ".1.conv1", K_CONV3, C, C, blk0_out, bufB, -1, 1, OUT_PLAIN, ln + ".1.conv1.weight", ln + ".1.bn1");
     add_conv(e, dn + ".1.conv2", K_CONV3, C, C, bufB, blk1_out, blk0_out, 1, mode, ln + ".1.conv2.weight", ln + ".1.bn2");
+    {
+      const int last = (int)e->layers.size() - 1;        // the stage's four convs form one chain
+      e->chains.push_back({last - 3, last - 2, last - 1, last});
+    }
     cur = blk1_out;
     if (stage < 4) { C *= 2; side /= 2; }
   }
@@ -523,23 +532,48 @@ struct ProfScope {                               // records a start/stop event p
   ~ProfScope() { if (on) cudaEventRecord(e->prof_ev.back(), st); }
 };
 
-int run_conv(flope_engine* e, ConvLayer& L, int n, cudaStream_t st) {
-  ProfScope ps(e, "conv:" + L.name, st);
-  ConvParams p = L.p;
-  p.n_positions = n * p.Hp * p.Wp;
-  p.wgt = L.d_w; p.bias = L.d_bias;
-  const int TM = L.mt * 128 * (L.pair ? 2 : 1);            // positions per (pair) tile
-  p.n_n_tiles = L.cout / L.n_tile;
-  // work items: (pair) tiles, or for the pooled stem quarter-crops (two per pair)
-  p.n_work = L.pool ? (n * p.pool_split + (L.pair ? 1 : 0)) / (L.pair ? 2 : 1) : (p.n_positions + TM - 1) / TM * p.n_n_tiles;
-  const int tiles = p.n_work;
-  dim3 grid((unsigned)(L.pair ? 2 * std::min(tiles, e->num_sms / 2) : std::min(tiles, e->num_sms)));
+// One launch of conv_igemm_kernel over `count` consecutive layers (a chain; count == 1 for a single layer).
+int run_convs(flope_engine* e, ConvLayer* const* Ls, int count, int n, cudaStream_t st, uint32_t* flags) {
+  ConvLayer& L0 = *Ls[0];
+  ProfScope ps(e, count == 1 ? "conv:" + L0.name : "conv:" + L0.name.substr(0, L0.name.find('.')) + " (chain of " + std::to_string(count) + ")", st);
+  ConvChain c;
+  std::memset(&c, 0, sizeof(c));
+  c.n_layers = count;
+  const int TM = L0.mt * 128 * (L0.pair ? 2 : 1);           // positions per (pair) tile
+  for (int i = 0; i < count; ++i) {
+    ConvLayer& L = *Ls[i];
+    ConvParams& p = c.L[i];
+    p = L.p;
+    p.n_positions = n * p.Hp * p.Wp;
+    p.wgt = L.d_w; p.bias = L.d_bias;
+    p.n_n_tiles = L.cout / L.n_tile;
+    // work items: (pair) tiles, or for the pooled stem row bands (two per pair)
+    p.n_work = L.pool ? (n * p.pool_split + (L.pair ? 1 : 0)) / (L.pair ? 2 : 1) : (p.n_positions + TM - 1) / TM * p.n_n_tiles;
+    p.res_layer = -1;
+    if (L.res_buf >= 0)
+      for (int j = 0; j < i; ++j)
+        if (Ls[j]->out_buf == L.res_buf) p.res_layer = j;  // the residual is produced inside this launch
+    if (L.n_tile != L0.n_tile || L.mt != L0.mt || L.pair != L0.pair || p.kc8 != L0.p.kc8 || p.halo_before != L0.p.halo_before ||
+        p.halo_after != L0.p.halo_after || p.n_a_slots != L0.p.n_a_slots || p.n_b_slots != L0.p.n_b_slots || L.cout != L0.cout ||
+        p.Hp != L0.p.Hp || p.Wp != L0.p.Wp)
+      return fail(FLOPE_EINVAL, "layers of a chain must share tile configuration and geometry: " + L.name);
+  }
+  c.n_m_tiles = c.L[0].n_work / c.L[0].n_n_tiles;
+  c.flags = count > 1 ? flags : nullptr;
+  c.expected = (uint32_t)(c.L[0].n_n_tiles * (L0.pair ? 2 : 1));
+  const int tiles = c.L[0].n_work * count;
+  dim3 grid((unsigned)(L0.pair ? 2 * std::min(tiles, e->num_sms / 2) : std::min(tiles, e->num_sms)));
   cudaError_t ce = cudaSuccess;
-  const int taps = L.kind == K_STEM ? 16 : 0;   // the stem's 4x4 window is issued a row of taps at a time
-  if (!conv_launch(L.n_tile, L.mt, L.pair, taps, p, grid, L.smem, st, e->use_pdl, &ce)) return fail(FLOPE_EINVAL, "no kernel instance for " + L.name);
-  if (ce != cudaSuccess) return fail(FLOPE_ECUDA, "launch of " + L.name + ": " + cudaGetErrorString(ce));
+  const int taps = L0.kind == K_STEM ? 16 : 0;   // the stem's 4x4 window is issued a row of taps at a time
+  if (!conv_launch(L0.n_tile, L0.mt, L0.pair, taps, c, grid, L0.smem, st, e->use_pdl, &ce)) return fail(FLOPE_EINVAL, "no kernel instance for " + L0.name);
+  if (ce != cudaSuccess) return fail(FLOPE_ECUDA, "launch of " + L0.name + ": " + cudaGetErrorString(ce));
   ++e->launches;
   return FLOPE_OK;
+}
+
+int run_conv(flope_engine* e, ConvLayer& L, int n, cudaStream_t st) {
+  ConvLayer* one[1] = {&L};
+  return run_convs(e, one, 1, n, st, nullptr);
 }
 
 int grid_for(long long total, int block) {
@@ -553,6 +587,7 @@ int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
   size_t li = 0;
   // mode 2: the stem .. layer4 conv_igemm launches as they run in production (back to back, programmatic
   // dependent launch overlapping each prologue with its predecessor's tail) between ONE pair of events
+  if (e->use_chain && e->d_flags) CUDA_TRY(cudaMemsetAsync(e->d_flags, 0, e->chains.size() * e->flags_per_chain * sizeof(uint32_t), st));
   std::unique_ptr<ProfScope> chain(new ProfScope(e, "conv_chain", st, 2));
   if (e->fuse_pool) {
     ++li;
@@ -566,8 +601,19 @@ int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
     launch_k(maxpool3x3s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, 1, e->use_pdl, a.d, a.g, b.d, b.g, n);
     ++e->launches;
   }
-  for (; li + 1 < e->layers.size(); ++li)
-    if ((rc = run_conv(e, e->layers[li], n, st))) return rc;
+  if (e->use_chain && !e->chains.empty()) {
+    // one launch per stage: its four convs as a layer-major stream of tiles, tile-level dependencies through flags
+    for (size_t ci = 0; ci < e->chains.size(); ++ci) {
+      ConvLayer* Ls[kMaxChain];
+      const int cnt = (int)e->chains[ci].size();
+      for (int i = 0; i < cnt; ++i) Ls[i] = &e->layers[e->chains[ci][i]];
+      if ((rc = run_convs(e, Ls, cnt, n, st, e->d_flags + ci * e->flags_per_chain))) return rc;
+    }
+    li = e->layers.size() - 1;
+  } else {
+    for (; li + 1 < e->layers.size(); ++li)
+      if ((rc = run_conv(e, e->layers[li], n, st))) return rc;
+  }
   chain.reset();
   {
     const ActBuf& a = e->bufs[e->buf_pool_in];
@@ -708,6 +754,16 @@ int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_
   for (ConvLayer& L : e->layers)
     if ((rc = plan_conv(e, L))) { flope_engine_destroy(e); return rc; }
   if (e->can_fuse_pool && (rc = plan_conv(e, e->stem_pool))) { flope_engine_destroy(e); return rc; }
+  {
+    // completion counters of the chains: kMaxChain layers x position tiles at max_batch (the smallest tile is 128 positions)
+    size_t per = 0;
+    for (const auto& ch : e->chains) {
+      const ConvParams& p = e->layers[ch[0]].p;
+      per = std::max(per, (size_t)kMaxChain * ((size_t)e->max_batch * p.Hp * p.Wp / 128 + 2));
+    }
+    e->flags_per_chain = per;
+    if (per) CUDA_TRY(cudaMalloc(&e->d_flags, e->chains.size() * per * sizeof(uint32_t)));
+  }
   CUDA_TRY(cudaDeviceSynchronize());
   *out = e;
   return FLOPE_OK;
@@ -721,6 +777,7 @@ void flope_engine_destroy(flope_engine* e) {
   for (ActBuf& b : e->bufs) cudaFree(b.d);
   for (ConvLayer& L : e->layers) { cudaFree(L.d_w); cudaFree(L.d_bias); }
   cudaFree(e->stem_pool.d_w); cudaFree(e->stem_pool.d_bias);
+  cudaFree(e->d_flags);
   cudaFree(e->d_feat); cudaFree(e->d_wrot); cudaFree(e->d_brot); cudaFree(e->d_r9);
   delete e;
 }
@@ -1026,6 +1083,7 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
     e->roi_strip = value;
     return FLOPE_OK;
   }
+  if (!std::strcmp(key, "chain")) { e->use_chain = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "pdl")) { e->use_pdl = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "pair") || !std::strcmp(key, "small_tiles")) {   // re-plans every layer; the packed weights depend on it: reload them
     if (key[0] == 'p') e->use_pair = value != 0; else e->small_tiles = value != 0;
