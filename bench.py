@@ -260,8 +260,9 @@ def run_ours(args):
         step(i, 0)
     pool.join()
     launches_per_step = 0
-    eng.posenet_forward(xs[0], out=r9)
-    launches_per_step += eng.last_launches() + 1                                       # + the pose-head launch
+    pool.engines[0].posenet_forward(xs[0], out=r9s[0])                                 # the engines the timed steps run on
+    launches_per_step += pool.engines[0].last_launches() + 1                           # + the pose-head launch
+    torch.cuda.synchronize()
     gathered = torch.empty((world, K, B, 9), dtype=torch.float64, device=dev) if world > 1 else None
 
     uuid = str(torch.cuda.get_device_properties(local).uuid)
