@@ -28,6 +28,10 @@
 //   empty barriers: tcgen05.commit multicast arrives in both CTAs
 //   accumulator   : acc_full by multicast commit; acc_empty lives in the leader (both CTAs' epilogue warps arrive)
 //
+// CHAIN (struct ConvChain below): the four convs of a ResNet stage in one launch, work items ordered layer-major, tile
+// (l, t) waiting on the completion counters of tiles (l-1, t-1 .. t+1): a layer's last partial wave and the next layer's
+// first wave run together instead of draining the machine at every layer boundary.
+//
 // TAPS: 16 = the stem's 4x4 window (K = 16 per tap, so only MT MMAs per tap): the MMA warp issues one window row
 // (4 taps) per loop iteration with arithmetic shifts; 0 = per-group tap tables (3x3, stride-2 phases, fc).
 //
