@@ -94,21 +94,26 @@ cudaError_t conv_set_attr() {
 // Launch with optional cluster size and programmatic dependent launch (the kernel may begin while its stream
 // predecessor drains; every kernel here calls griddep_wait() before touching activations).
 template <typename... KArgs, typename... Args>
-cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, bool pdl,
-                     Args&&... args) {
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, int pdl,
+                     Args&&... args) {   // pdl: bit 0 = programmatic dependent launch, bit 1 = cooperative launch
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int na = 0;
+  if (pdl & 2) {                                          // cooperative: the whole grid becomes resident at once or not at all
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
   if (cluster > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;   // the two CTAs of a pair share a TPC
     attr[na].val.clusterDim.x = cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl) {
+  if (pdl & 1) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -119,7 +124,7 @@ cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 
 template <int N_TILE, int MT, int KP, bool POOL, bool PAIR, int TAPS>
-cudaError_t conv_launch_t(const ConvChain& c, dim3 grid, size_t smem, cudaStream_t st, bool pdl) {
+cudaError_t conv_launch_t(const ConvChain& c, dim3 grid, size_t smem, cudaStream_t st, int pdl) {
   return launch_k(conv_igemm_kernel<N_TILE, MT, KP, POOL, PAIR, TAPS>, grid, dim3(kConvThreads), smem, st, PAIR ? 2 : 1, pdl, c);
 }
 
@@ -141,7 +146,7 @@ cudaError_t conv_set_all_attrs() {
   return cudaSuccess;
 }
 // returns false when no kernel instance matches; *err receives the launch status otherwise
-bool conv_launch(int n_tile, int mt, bool pair, int taps, const ConvChain& c, dim3 grid, size_t smem, cudaStream_t st, bool pdl,
+bool conv_launch(int n_tile, int mt, bool pair, int taps, const ConvChain& c, dim3 grid, size_t smem, cudaStream_t st, int pdl,
                  cudaError_t* err) {
   const ConvParams& p = c.L[0];
 #define X(N, M, K, P, R, T)                                                                                        \
@@ -165,6 +170,7 @@ struct flope_engine {
   std::vector<ConvLayer> layers;
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
   int roi_strip = 14;                            // output rows per CTA of the bilinear ROI kernel (even; crops below 448 px)
+  bool chain_coop = false;                       // launch chains cooperatively (gang-scheduled): needed when several engines share a device
   bool use_chain = true;                         // one persistent launch per ResNet stage (four convs) with per-tile completion flags
   std::vector<std::vector<int>> chains;          // layer indices of each stage
   uint32_t* d_flags = nullptr;                   // completion counters of all chains, zeroed at the start of every forward
@@ -565,7 +571,9 @@ int run_convs(flope_engine* e, ConvLayer* const* Ls, int count, int n, cudaStrea
   dim3 grid((unsigned)(L0.pair ? 2 * std::min(tiles, e->num_sms / 2) : std::min(tiles, e->num_sms)));
   cudaError_t ce = cudaSuccess;
   const int taps = L0.kind == K_STEM ? 16 : 0;   // the stem's 4x4 window is issued a row of taps at a time
-  if (!conv_launch(L0.n_tile, L0.mt, L0.pair, taps, c, grid, L0.smem, st, e->use_pdl, &ce)) return fail(FLOPE_EINVAL, "no kernel instance for " + L0.name);
+  // bit 0: programmatic dependent launch; bit 1: cooperative launch (chains of engines that share the device)
+  const int launch_mode = (e->use_pdl ? 1 : 0) | ((count > 1 && e->chain_coop) ? 2 : 0);
+  if (!conv_launch(L0.n_tile, L0.mt, L0.pair, taps, c, grid, L0.smem, st, launch_mode, &ce)) return fail(FLOPE_EINVAL, "no kernel instance for " + L0.name);
   if (ce != cudaSuccess) return fail(FLOPE_ECUDA, "launch of " + L0.name + ": " + cudaGetErrorString(ce));
   ++e->launches;
   return FLOPE_OK;
@@ -1083,6 +1091,7 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
     e->roi_strip = value;
     return FLOPE_OK;
   }
+  if (!std::strcmp(key, "chain_coop")) { e->chain_coop = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "chain")) { e->use_chain = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "pdl")) { e->use_pdl = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "pair") || !std::strcmp(key, "small_tiles")) {   // re-plans every layer; the packed weights depend on it: reload them

@@ -12,6 +12,8 @@ x = [torch.rand((B, 3, S, S), device="cuda") for _ in range(2)]
 for ne in [int(v) for v in sys.argv[3:]] or [1, 2, 3]:
     engs = [_lib.Engine(0, max_batch=B, crop_hw=S) for _ in range(ne)]
     for e in engs:
+        for kv in filter(None, os.environ.get("FLOPE_SET", "").split(",")):
+            e.debug_set(kv.split("=")[0], int(kv.split("=")[1]))
         e.load_state_dict(sd)
     streams = [torch.cuda.Stream() for _ in range(ne)]
     outs = [torch.empty((B, 9), device="cuda") for _ in range(ne)]

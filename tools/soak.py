@@ -11,6 +11,9 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 ne = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 dev = torch.device("cuda:0")
 pool = EnginePool(dev, n_engines=ne, max_batch=B, crop_hw=224, state_dict=synth.random_state_dict(0))
+for kv in filter(None, os.environ.get("FLOPE_SET", "").split(",")):      # e.g. FLOPE_SET=chain_coop=0 (no re-pack needed)
+    for e in pool.engines:
+        e.debug_set(kv.split("=")[0], int(kv.split("=")[1]))
 xs = [synth.mixed_crops(B, 224, seed=100 + i).to(dev) for i in range(2)]
 outs = [[torch.empty((B, 9), device=dev) for _ in range(2)] for _ in range(ne)]
 ref = []
