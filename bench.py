@@ -432,7 +432,7 @@ def run_ours(args):
     eng.profile(2)
     for i in range(prof_steps):
         eng.posenet_forward(xs[i & 1], out=r9)
-    chain = [t for name, t in eng.profile_read() if name == "conv_chain"]
+    chain = [t for name, t in eng.profile_read() if name == "trunk"]
     eng.profile(False)
     chain_ms = sorted(chain)[len(chain) // 2]
     eng.profile(1)
@@ -465,7 +465,7 @@ def run_ours(args):
                           "(median of %d steps); avg launch duration = chain / launches" % prof_steps,
                 "launches": chain_launches, "avg_launch_ms": chain_ms / max(chain_launches, 1),
                 "algorithmic_flop_per_launch": (flop - fc_flop) / max(chain_launches, 1),
-                "algorithmic_flop_per_step": flop, "conv_chain_ms_per_step": chain_ms,
+                "algorithmic_flop_per_step": flop, "trunk_ms_per_step": chain_ms,
                 "achieved_isolated_launches": achieved_iso, "frac_isolated_launches": achieved_iso / peaks["tf_burst"],
                 "conv_ms_per_step_isolated": conv_ms,
                 "all_kernels_ms_per_step_isolated": all_ms, "conv_share_of_step": chain_ms / (ms_serial / K),

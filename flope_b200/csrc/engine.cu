@@ -593,10 +593,10 @@ int grid_for(long long total, int block) {
 int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
   int rc;
   size_t li = 0;
-  // mode 2: the stem .. layer4 conv_igemm launches as they run in production (back to back, programmatic
-  // dependent launch overlapping each prologue with its predecessor's tail) between ONE pair of events
+  // mode 2: the stem .. layer4 conv_igemm launches (the trunk) as they run in production - back to back, programmatic
+  // dependent launch overlapping each prologue with its predecessor's tail - between ONE pair of events
   if (e->use_chain && e->d_flags) CUDA_TRY(cudaMemsetAsync(e->d_flags, 0, e->chains.size() * e->flags_per_chain * sizeof(uint32_t), st));
-  std::unique_ptr<ProfScope> chain(new ProfScope(e, "conv_chain", st, 2));
+  std::unique_ptr<ProfScope> trunk(new ProfScope(e, "trunk", st, 2));
   if (e->fuse_pool) {
     ++li;
     if ((rc = run_conv(e, e->stem_pool, n, st))) return rc;   // stem conv + BN + ReLU + max-pool in one kernel
@@ -622,7 +622,7 @@ int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
     for (; li + 1 < e->layers.size(); ++li)
       if ((rc = run_conv(e, e->layers[li], n, st))) return rc;
   }
-  chain.reset();
+  trunk.reset();
   {
     const ActBuf& a = e->bufs[e->buf_pool_in];
     const ActBuf& b = e->bufs[e->buf_pool];

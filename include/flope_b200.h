@@ -134,8 +134,8 @@ int flope_engine_last_launches(const flope_engine* e);
 /* CUDA-event timing for bench.py's roofline pass.  flope_engine_profile(e,1) clears and enables
  * recording of one start/stop event pair around every kernel launch of subsequent calls (isolated
  * launches: the events between kernels prevent programmatic-dependent-launch overlap);
- * flope_engine_profile(e,2) records ONE pair around the trunk's conv_igemm chain (stem .. layer4, the
- * launches back to back exactly as in production, entry name "conv_chain"); 0 disables.
+ * flope_engine_profile(e,2) records ONE pair around the trunk's conv_igemm launches (stem .. layer4, the
+ * launches back to back exactly as in production, entry name "trunk"); 0 disables.
  * flope_engine_profile_read synchronises the device and returns the number of recorded launches,
  * their names as a '\n'-joined string and their durations in milliseconds. */
 int flope_engine_profile(flope_engine* e, int enable);
