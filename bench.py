@@ -421,9 +421,10 @@ def run_ours(args):
                     "us_per_launch": roi_ms * 1e3, "l2": "flushed (256 MB write) before every timed launch"}
 
     # ---- roofline of the dominant kernel family (conv_igemm_kernel: every trunk layer, stem+pool .. layer4) ----
-    # (a) chain: ONE CUDA-event pair on the launch stream around the 17 trunk launches of a step, issued back to
-    #     back exactly as the product runs them (programmatic dependent launch overlaps each prologue with the
-    #     previous kernel's tail); average launch duration = chain time / launches.  This is `achieved`.
+    # (a) trunk: ONE CUDA-event pair on the launch stream around the trunk launches of a step (fused stem+max-pool and
+    #     one chain per ResNet stage), issued back to back exactly as the product runs them (programmatic dependent
+    #     launch overlaps each prologue with the previous kernel's tail); average launch duration = trunk time /
+    #     launches.  This is `achieved`.
     # (b) isolated: an event pair around every single launch (events between kernels serialise them and expose
     #     every prologue/tail) - reported next to it and used for the per-kernel table.
     flop = FLOP_PER_CROP.get(S, 3.6293e9 * (S / 224.0) ** 2) * B
@@ -456,13 +457,13 @@ def run_ours(args):
         except Exception:
             traffic = None
     roofline = {"bound": "tensor",
-                "kernel": "conv_igemm_kernel (the %d trunk launches of one step: stem+maxpool, layer1..layer4; fc excluded)" % chain_launches,
+                "kernel": "conv_igemm_kernel (the %d trunk launches of one step: fused stem+maxpool, one chain of four convs per ResNet stage; fc excluded)" % chain_launches,
                 "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
                 "frac_of_sustained_peak": achieved / peaks["tf_sust"] if peaks["tf_sust"] else None,
                 "peak_source": peaks["src"] + " (MEASURED_PEAKS.json burst bf16)" if peaks["src"] == "measured" else "fallback 1.59 PFLOP/s",
                 "traffic": traffic,
-                "method": "algorithmic FLOP of the trunk / CUDA-event time of the back-to-back launch chain on the launch stream "
-                          "(median of %d steps); avg launch duration = chain / launches" % prof_steps,
+                "method": "algorithmic FLOP of the trunk / CUDA-event time of its back-to-back launches on the launch stream "
+                          "(median of %d steps); avg launch duration = trunk time / launches" % prof_steps,
                 "launches": chain_launches, "avg_launch_ms": chain_ms / max(chain_launches, 1),
                 "algorithmic_flop_per_launch": (flop - fc_flop) / max(chain_launches, 1),
                 "algorithmic_flop_per_step": flop, "trunk_ms_per_step": chain_ms,
