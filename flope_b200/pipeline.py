@@ -12,17 +12,21 @@ from . import _lib
 
 
 class EnginePool:
-    def __init__(self, device, n_engines=2, max_batch=256, crop_hw=224, state_dict=None):
+    def __init__(self, device, n_engines=2, max_batch=256, crop_hw=224, state_dict=None, cooperative_chains=False):
         self.device = torch.device(device)
         idx = self.device.index or 0
         self.engines = [_lib.Engine(idx, max_batch, crop_hw) for _ in range(n_engines)]
         if n_engines > 1:
             # Stage chains (one persistent launch per ResNet stage whose tiles wait for each other) need every CTA of a
             # chain kernel to become resident.  Two chain kernels from two streams could each hold part of the SMs while
-            # waiting for their own unscheduled CTAs, so engines that run concurrently launch their chains cooperatively
-            # (gang-scheduled: the whole grid at once or not at all; ~1 % slower than a plain launch).
+            # waiting for their own unscheduled CTAs, so engines that run concurrently either launch one kernel per
+            # layer (default) or launch their chains cooperatively (gang-scheduled grids; 1 % faster than per-layer
+            # launches, but Nsight Compute cannot profile cooperative cluster launches: "LaunchFailed").
             for e in self.engines:
-                e.debug_set("chain_coop", 1)
+                if cooperative_chains:
+                    e.debug_set("chain_coop", 1)
+                else:
+                    e.debug_set("chain", 0)
         if state_dict is not None:
             for e in self.engines:
                 e.load_state_dict(state_dict)

@@ -17,7 +17,7 @@
  * launch their stage chains cooperatively (flope_debug_set(e, "chain_coop", 1)) or switch them off
  * ("chain", 0): a chain kernel's tiles wait for each other and rely on all of its CTAs becoming
  * resident, which two such kernels competing for the SMs do not guarantee unless the launch is
- * gang-scheduled (flope_b200.pipeline.EnginePool sets chain_coop for its engines).
+ * gang-scheduled (flope_b200.pipeline.EnginePool switches the chains of its engines off by default).
  */
 #ifndef FLOPE_B200_H
 #define FLOPE_B200_H
