@@ -66,6 +66,24 @@ def test_no_cpu_fallback():
     from flope_b200.conversion import procrustes_to_rotmat
     with pytest.raises(_lib.FlopeError):
         procrustes_to_rotmat(torch.zeros(2, 9))
+    from flope_b200 import image_manipulation as im
+    from flope_b200.pipeline import EnginePool
+    with pytest.raises(_lib.FlopeError):
+        im.get_depth_value(np.zeros((1, 4), np.int32), np.ones((8, 8), np.float32), np.zeros((8, 8), np.uint8))
+    with pytest.raises(_lib.FlopeError):
+        im.shrink_mask(np.ones((8, 8), bool), 3)
+    with pytest.raises(_lib.FlopeError):
+        EnginePool("cuda:0", n_engines=2, max_batch=4, crop_hw=64)
+    with pytest.raises(_lib.FlopeError):
+        _lib.yolo_mask(torch.zeros((1, 8, 8)), 16, 16)
+    with pytest.raises(_lib.FlopeError):
+        _lib.depth_values(torch.zeros((8, 8)), torch.zeros((8, 8), dtype=torch.uint8), torch.zeros((0, 4), dtype=torch.int32), 0.1, 2.5)
+
+
+def test_new_entry_points_reject_bad_arguments(L):
+    """The stateless device entry points validate their arguments before touching CUDA (codes, not crashes)."""
+    assert L.flope_depth_values(0, None, 0, 1.0, None, 8, 8, None, 0, 0.1, 2.5, 10, None, None, None, None) == -1
+    assert L.flope_yolo_mask(0, None, 1, 8, 8, None, None, 16, 16, None, None) == -1
 
 
 def test_product_never_imports_oracle():
