@@ -171,6 +171,7 @@ struct flope_engine {
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
   int roi_strip = 14;                            // output rows per CTA of the bilinear ROI kernel (even; crops below 448 px)
   bool chain_coop = false;                       // launch chains cooperatively (gang-scheduled): needed when several engines share a device
+  int chain_dynamic = 0;                     // chains claim work items from an atomic counter (safe under partial residency)
   bool use_chain = true;                         // one persistent launch per ResNet stage (four convs) with per-tile completion flags
   std::vector<std::vector<int>> chains;          // layer indices of each stage
   uint32_t* d_flags = nullptr;                   // completion counters of all chains, zeroed at the start of every forward
@@ -539,6 +540,9 @@ struct ProfScope {                               // records a start/stop event p
 };
 
 // One launch of conv_igemm_kernel over `count` consecutive layers (a chain; count == 1 for a single layer).
+constexpr size_t kChainHeader = 2048;           // uint32 words ahead of a chain's tile flags (claim counter + hand-over slots)
+static_assert(kChainHeader / 2 >= 74 * kClaimRing, "hand-over slots for every CTA");
+
 int run_convs(flope_engine* e, ConvLayer* const* Ls, int count, int n, cudaStream_t st, uint32_t* flags) {
   ConvLayer& L0 = *Ls[0];
   ProfScope ps(e, count == 1 ? "conv:" + L0.name : "conv:" + L0.name.substr(0, L0.name.find('.')) + " (chain of " + std::to_string(count) + ")", st);
@@ -565,7 +569,11 @@ int run_convs(flope_engine* e, ConvLayer* const* Ls, int count, int n, cudaStrea
       return fail(FLOPE_EINVAL, "layers of a chain must share tile configuration and geometry: " + L.name);
   }
   c.n_m_tiles = c.L[0].n_work / c.L[0].n_n_tiles;
-  c.flags = count > 1 ? flags : nullptr;
+  // chain scratch: [0] claim counter, [kChainHeader/2 ..) claim hand-over slots, [kChainHeader ..) tile flags
+  c.flags = count > 1 ? flags + kChainHeader : nullptr;
+  c.counter = (count > 1 && e->chain_dynamic) ? flags : nullptr;
+  c.claim_static = e->chain_dynamic == 2;
+  c.claims = (count > 1 && e->chain_dynamic) ? flags + kChainHeader / 2 : nullptr;
   c.expected = (uint32_t)(c.L[0].n_n_tiles * (L0.pair ? 2 : 1));
   const int tiles = c.L[0].n_work * count;
   dim3 grid((unsigned)(L0.pair ? 2 * std::min(tiles, e->num_sms / 2) : std::min(tiles, e->num_sms)));
@@ -767,7 +775,7 @@ int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_
     size_t per = 0;
     for (const auto& ch : e->chains) {
       const ConvParams& p = e->layers[ch[0]].p;
-      per = std::max(per, (size_t)kMaxChain * ((size_t)e->max_batch * p.Hp * p.Wp / 128 + 2));
+      per = std::max(per, kChainHeader + (size_t)kMaxChain * ((size_t)e->max_batch * p.Hp * p.Wp / 128 + 2));
     }
     e->flags_per_chain = per;
     if (per) CUDA_TRY(cudaMalloc(&e->d_flags, e->chains.size() * per * sizeof(uint32_t)));
@@ -1092,6 +1100,7 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
     return FLOPE_OK;
   }
   if (!std::strcmp(key, "chain_coop")) { e->chain_coop = value != 0; drop_graphs(e); return FLOPE_OK; }
+  if (!std::strcmp(key, "chain_dynamic")) { e->chain_dynamic = value; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "chain")) { e->use_chain = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "pdl")) { e->use_pdl = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "pair") || !std::strcmp(key, "small_tiles")) {   // re-plans every layer; the packed weights depend on it: reload them

@@ -14,8 +14,8 @@
  * output buffer; the engine owns weights and workspace sized by max_batch.  One engine per
  * (device, stream): calls on different engines may run concurrently, calls on one engine
  * may not.  Engines whose kernels can be in flight on the SAME device at the same time must
- * launch their stage chains cooperatively (flope_debug_set(e, "chain_coop", 1)) or switch them off
- * ("chain", 0): a chain kernel's tiles wait for each other and rely on all of its CTAs becoming
+ * launch their stage chains cooperatively (flope_debug_set(e, "chain_coop", 1)), let them claim
+ * their work dynamically ("chain_dynamic", 1) or switch them off ("chain", 0): a chain kernel's tiles wait for each other and rely on all of its CTAs becoming
  * resident, which two such kernels competing for the SMs do not guarantee unless the launch is
  * gang-scheduled (flope_b200.pipeline.EnginePool switches the chains of its engines off by default).
  */
@@ -156,6 +156,9 @@ int flope_debug_normalise_lut(float* d_out, void* stream);
  *   "chain"       0/1  one persistent launch per ResNet stage (four convs, per-tile dependencies) instead of one
  *                      launch per layer (default 1; see the concurrency note at the top)
  *   "chain_coop"  0/1  launch the chains cooperatively (default 0; required when engines share a device)
+ *   "chain_dynamic" 0/1  chains claim their work items in index order from an atomic counter instead of
+ *                      round-robin by block index: safe under partial residency without a cooperative launch
+ *                      (default 0: 3 % slower than the static deal on a single stream)
  *   "pair"        0/1  CTA-pair (tcgen05 cta_group::2) conv kernels instead of single-CTA ones (default 1)
  *   "small_tiles" 0/1  latency-oriented tiles when max_batch cannot fill the SMs (default 1)
  * "pair" and "small_tiles" change the packed-weight layout: call flope_engine_load_weights again afterwards.

@@ -191,3 +191,42 @@ def test_graph_replay_equals_direct_launches(eng224):
     c = eng224.posenet_forward(x).clone()      # replays
     torch.cuda.synchronize()
     assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_chain_scheduling_modes_agree_bitwise(cuda_lib, net):
+    """Per-layer launches, stage chains with the static round-robin deal, and stage chains that claim their work
+    items from an atomic counter compute every tile with the same arithmetic: identical bits, single-CTA and pair
+    kernels, also with two engines on two streams in flight (dynamic claiming is the mode that is safe there
+    without a cooperative launch)."""
+    x = synth.mixed_crops(75, 224).cuda()
+    x = torch.cat([x, x.flip(0), x.roll(7, 0), x.flip(3)], 0)
+    engs = [cuda_lib.Engine(0, max_batch=300, crop_hw=224) for _ in range(2)]
+    try:
+        for pair in (1, 0):
+            for e in engs:
+                e.debug_set("pair", pair)
+                e.load_state_dict(net.state_dict())
+            e = engs[0]
+            e.debug_set("chain", 0)
+            ref = e.posenet_forward(x).clone()
+            e.debug_set("chain", 1)
+            for dyn in (0, 1):
+                e.debug_set("chain_dynamic", dyn)
+                for _ in range(3):                      # direct launches, graph capture, graph replay
+                    assert torch.equal(e.posenet_forward(x), ref), (pair, dyn)
+            for e in engs:
+                e.debug_set("chain_dynamic", 1)
+            streams = [torch.cuda.Stream() for _ in engs]
+            torch.cuda.synchronize()
+            outs = []
+            for i in range(12):
+                with torch.cuda.stream(streams[i & 1]):
+                    outs.append(engs[i & 1].posenet_forward(x).clone())
+            torch.cuda.synchronize()
+            for o in outs:
+                assert torch.equal(o, ref), pair
+            for e in engs:
+                e.debug_set("chain_dynamic", 0)
+    finally:
+        for e in engs:
+            e.close()
