@@ -76,9 +76,11 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, Geom g
   }
 }
 
-// One warp per (c8 plane, crop): lanes stride over the H*W pixels (16-byte loads), fp32 partial sums,
-// xor-shuffle reduction; lane 0 writes the bf16 means into the "one pixel per crop" blocked tensor the
-// fc GEMM reads (plane c8, position = crop index).
+// One warp per (c8 plane, crop): the crop's Hp*Wp positions of a plane are contiguous and its padding positions
+// hold zeros (the layout's invariant - every conv relies on it), so the lanes stride over ALL of them with 16-byte
+// loads and no index arithmetic; fp32 partial sums; a reduce-scatter over the lanes (each xor step halves the
+// channels a lane still carries: 4+2+1+1+1 shuffles instead of 8x5); lane 0 writes the bf16 means into the "one
+// pixel per crop" blocked tensor the fc GEMM reads (plane c8, position = crop index).
 __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ in, Geom gi, __nv_bfloat16* __restrict__ out,
                                Geom go, int n) {
   griddep_wait();
@@ -90,25 +92,42 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ in, Geom gi, __
   const int b = wid % n;
   const int c8 = wid / n;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const __nv_bfloat16* src = in + ((long long)c8 * gi.plane + gi.base) * 8;
-  const int hw = gi.H * gi.W;
-  for (int i = lane; i < hw; i += 32) {
-    const int h = i / gi.W, w = i - h * gi.W;
-    const uint4 v = *reinterpret_cast<const uint4*>(src + geom_pos(gi, b, h, w) * 8);
+  const int img = gi.Hp * gi.Wp;
+  const uint4* src = reinterpret_cast<const uint4*>(in + ((long long)c8 * gi.plane + gi.base + (long long)b * img) * 8);
+  for (int i = lane; i < img; i += 32) {
+    const uint4 v = src[i];
     s[0] += bf16_lo(v.x); s[1] += bf16_hi(v.x); s[2] += bf16_lo(v.y); s[3] += bf16_hi(v.y);
     s[4] += bf16_lo(v.z); s[5] += bf16_hi(v.z); s[6] += bf16_lo(v.w); s[7] += bf16_hi(v.w);
   }
+  // lanes with bit 4 set keep channels 4..7, the others 0..3; then bit 3 splits those four into two, bit 2 into one
+  float t4[4], t2[2], t1;
+  {
+    const bool hi = lane & 16;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    for (int j = 0; j < 4; ++j) {
+      const float give = hi ? s[j] : s[4 + j], keep = hi ? s[4 + j] : s[j];
+      t4[j] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+    }
   }
-  if (lane == 0) {
-    const float inv = 1.0f / (float)hw;
-    uint4 o;
-    o.x = pack_bf16x2(s[0] * inv, s[1] * inv); o.y = pack_bf16x2(s[2] * inv, s[3] * inv);
-    o.z = pack_bf16x2(s[4] * inv, s[5] * inv); o.w = pack_bf16x2(s[6] * inv, s[7] * inv);
-    *reinterpret_cast<uint4*>(out + ((long long)c8 * go.plane + go.base + b) * 8) = o;
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float give = hi ? t4[j] : t4[2 + j], keep = hi ? t4[2 + j] : t4[j];
+      t2[j] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+    const float give = hi ? t2[0] : t2[1], keep = hi ? t2[1] : t2[0];
+    t1 = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+  }
+  t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+  t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+  // lane 4*ch (ch = 0..7) now holds the sum of channel ch: 4*bit4 + 2*bit3 + bit2 of the lane index
+  if (!(lane & 3)) {
+    const int ch = lane >> 2;
+    out[((long long)c8 * go.plane + go.base + b) * 8 + ch] = __float2bfloat16_rn(t1 * (1.0f / (float)(gi.H * gi.W)));
   }
 }
 
