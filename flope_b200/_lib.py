@@ -19,7 +19,7 @@ SYMBOLS = [
     "flope_version", "flope_last_error", "flope_engine_create", "flope_engine_destroy",
     "flope_engine_load_weights", "flope_squarify_filter", "flope_roi_crop", "flope_posenet_forward",
     "flope_pose_head", "flope_nullify_yaw", "flope_infer_frames", "flope_engine_last_launches",
-    "flope_debug_activation", "flope_debug_normalise_lut", "flope_debug_set",
+    "flope_debug_activation", "flope_debug_normalise_lut", "flope_debug_set", "flope_debug_timeline",
     "flope_engine_profile", "flope_engine_profile_read", "flope_depth_values", "flope_yolo_mask",
 ]
 
@@ -60,6 +60,7 @@ def lib():
         L.flope_debug_activation.restype = C.c_int64
         L.flope_debug_normalise_lut.argtypes = [C.c_void_p, C.c_void_p]
         L.flope_debug_set.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.flope_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.flope_engine_profile.argtypes = [C.c_void_p, C.c_int]
         L.flope_engine_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.c_int]
         L.flope_depth_values.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
@@ -254,6 +255,14 @@ class Engine:
         buf = torch.empty((n * 64 * (S // 2) * (S // 2),), dtype=torch.float32, device=f"cuda:{self.device}")
         chw = check(lib().flope_debug_activation(self._h, name.encode(), n, _ptr(buf), _stream()))
         return buf[: n * chw], chw
+
+    def timeline(self, max_launches=32):
+        """Phase stamps of the conv launches of the last forward: uint64 array (launches, 148, 8); needs
+        debug_set("timeline", 1).  See flope_debug_timeline in include/flope_b200.h."""
+        import numpy as np
+        buf = np.zeros((max_launches, 148, 8), np.uint64)
+        n = check(lib().flope_debug_timeline(self._h, buf.ctypes.data, max_launches))
+        return buf[:n]
 
     def debug_set(self, key, value):
         check(lib().flope_debug_set(self._h, key.encode(), int(value)))

@@ -126,8 +126,14 @@ struct ConvChain {
   // even when the grid is only partly resident (several engines sharing the device), without a cooperative launch.
   uint32_t* counter;           // next unclaimed item, zeroed before the launch (nullptr: static round-robin)
   int claim_static;
+  // Optional phase stamps (diagnosis, tools/timeline.py): [CTA][kStampWords] = %globaltimer (ns) at entry, prologue
+  // done, dependency wait done, first operands landed, last MMA issued, first accumulator ready, last store issued,
+  // exit.  (Not clock64: the SM cycle counter was measured to advance at 0.45-0.85 of the SM clock over a CTA's
+  // life - it does not count while every warp of the SM is parked in a barrier wait.)  nullptr in production.
+  unsigned long long* stamps;
   uint32_t* claims;            // [CTA pairs][kClaimRing] leader -> peer hand-over of the claimed items (pair kernels)
 };
+constexpr int kStampWords = 8;
 constexpr int kClaimQ = 4;     // claimed items a CTA may hold ahead of its epilogue
 constexpr int kClaimRing = 8;  // hand-over slots per CTA pair (> kClaimQ + the claims in flight)
 
@@ -267,6 +273,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     return (n * p.Hp + q * p.pool_rows + 4 * (tt - 1)) * p.Wp;
   };
 
+  unsigned long long* stamps = ch.stamps ? ch.stamps + (size_t)blockIdx.x * kStampWords : nullptr;
+  auto stamp = [&](int i) {
+    if (!stamps) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    stamps[i] = t;
+  };
+  if (threadIdx.x == 0) stamp(0);
   if (threadIdx.x == 0) {
     const uint32_t full_count = (PAIR && rank == 0) ? 2u : 1u;   // leader: own producer + the peer's relay
     for (int i = 0; i < p.n_a_slots; ++i) { mbar_init(&a_full[i], full_count); mbar_init(&a_empty[i], 1); }
@@ -286,10 +300,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   if (PAIR) cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) stamp(1);
   // everything above touched only static data (bias) and on-chip state; the activations of the previous layer
   // are complete and visible after this point, and the next kernel may begin its own prologue
   griddep_wait();
   griddep_launch();
+  if (threadIdx.x == 0) stamp(2);
 
   if (warp == 0) {
     // ===================== TMA producer: whole warp runs the loop, one lane issues =====================
@@ -448,6 +464,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         };
         for (int g = 0; g < q.n_groups; ++g) {
           mbar_wait(&a_full[a_slot], a_phase);
+          if (it == 0 && g == 0 && lane == 0) stamp(3);
           const uint32_t a_grp = a_lo0 + a_slot * a_slot_units;
           const bool last_group = g == q.n_groups - 1;
           if (TAPS == 16) {
@@ -469,6 +486,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       }
       done_item(k);
     }
+    if (lane == 0) stamp(4);
   } else {
     // ===================== epilogue: kEpiWarps warps, 4 per TMEM lane quarter =====================
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read
@@ -599,6 +617,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             mbar_wait(&acc_full[stage], (it >> 1) & 1);
             tc_fence_after();
             waited = true;
+            if (it == 0 && threadIdx.x == 64) stamp(5);
           }
           uint32_t v32[32];
           tmem_ld32(acc + (uint32_t)(mt * N_TILE + c0), v32);
@@ -670,9 +689,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       }
       done_item(k);
     }
+    if (threadIdx.x == 64) stamp(6);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(7);
   if (PAIR) cluster_sync_all();            // the peer may still read this CTA's smem / signal its barriers until here
   if (warp == 1) {
     tc_fence_after();

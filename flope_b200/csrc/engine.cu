@@ -22,6 +22,7 @@
 #include "mask_post.cuh"
 #include "pointwise.cuh"
 #include "pose_head.cuh"
+#include "trunk_chain.cuh"
 #include "roi_crop.cuh"
 
 using namespace flope;
@@ -143,7 +144,7 @@ cudaError_t conv_set_all_attrs() {
 #define X(N, M, K, P, R, T) if ((e = conv_set_attr<N, M, K, P, R, T>()) != cudaSuccess) return e;
   FOR_EACH_CONV_CFG(X)
 #undef X
-  return cudaSuccess;
+  return cudaFuncSetAttribute(trunk_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
 }
 // returns false when no kernel instance matches; *err receives the launch status otherwise
 bool conv_launch(int n_tile, int mt, bool pair, int taps, const ConvChain& c, dim3 grid, size_t smem, cudaStream_t st, int pdl,
@@ -171,6 +172,9 @@ struct flope_engine {
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
   int roi_strip = 14;                            // output rows per CTA of the bilinear ROI kernel (even; crops below 448 px)
   bool chain_coop = false;                       // launch chains cooperatively (gang-scheduled): needed when several engines share a device
+  unsigned long long* d_stamps = nullptr;        // phase stamps of the conv launches of one forward ("timeline" debug option)
+  int stamp_launch = 0;
+  bool use_trunk = true;                         // layer1..layer4 as one launch when the plan allows (trunk_chain.cuh)
   int chain_dynamic = 0;                     // chains claim work items from an atomic counter (safe under partial residency)
   bool use_chain = true;                         // one persistent launch per ResNet stage (four convs) with per-tile completion flags
   std::vector<std::vector<int>> chains;          // layer indices of each stage
@@ -540,13 +544,13 @@ struct ProfScope {                               // records a start/stop event p
 };
 
 // One launch of conv_igemm_kernel over `count` consecutive layers (a chain; count == 1 for a single layer).
+constexpr int kStampLaunches = 32;              // conv launches of one forward the timeline keeps
 constexpr size_t kChainHeader = 2048;           // uint32 words ahead of a chain's tile flags (claim counter + hand-over slots)
 static_assert(kChainHeader / 2 >= 74 * kClaimRing, "hand-over slots for every CTA");
 
-int run_convs(flope_engine* e, ConvLayer* const* Ls, int count, int n, cudaStream_t st, uint32_t* flags) {
+// Kernel arguments of `count` consecutive layers run as one chain (count == 1: a single layer).
+int build_chain(flope_engine* e, ConvLayer* const* Ls, int count, int n, uint32_t* flags, ConvChain& c) {
   ConvLayer& L0 = *Ls[0];
-  ProfScope ps(e, count == 1 ? "conv:" + L0.name : "conv:" + L0.name.substr(0, L0.name.find('.')) + " (chain of " + std::to_string(count) + ")", st);
-  ConvChain c;
   std::memset(&c, 0, sizeof(c));
   c.n_layers = count;
   const int TM = L0.mt * 128 * (L0.pair ? 2 : 1);           // positions per (pair) tile
@@ -575,14 +579,67 @@ int run_convs(flope_engine* e, ConvLayer* const* Ls, int count, int n, cudaStrea
   c.claim_static = e->chain_dynamic == 2;
   c.claims = (count > 1 && e->chain_dynamic) ? flags + kChainHeader / 2 : nullptr;
   c.expected = (uint32_t)(c.L[0].n_n_tiles * (L0.pair ? 2 : 1));
+  return FLOPE_OK;
+}
+
+// One launch of conv_igemm_kernel over `count` consecutive layers (a chain; count == 1 for a single layer).
+int run_convs(flope_engine* e, ConvLayer* const* Ls, int count, int n, cudaStream_t st, uint32_t* flags) {
+  ConvLayer& L0 = *Ls[0];
+  ProfScope ps(e, count == 1 ? "conv:" + L0.name : "conv:" + L0.name.substr(0, L0.name.find('.')) + " (chain of " + std::to_string(count) + ")", st);
+  ConvChain c;
+  int rc;
+  if ((rc = build_chain(e, Ls, count, n, flags, c))) return rc;
   const int tiles = c.L[0].n_work * count;
   dim3 grid((unsigned)(L0.pair ? 2 * std::min(tiles, e->num_sms / 2) : std::min(tiles, e->num_sms)));
+  if (e->d_stamps && e->stamp_launch < kStampLaunches && grid.x <= 148) c.stamps = e->d_stamps + (size_t)e->stamp_launch++ * 148 * kStampWords;
   cudaError_t ce = cudaSuccess;
   const int taps = L0.kind == K_STEM ? 16 : 0;   // the stem's 4x4 window is issued a row of taps at a time
   // bit 0: programmatic dependent launch; bit 1: cooperative launch (chains of engines that share the device)
   const int launch_mode = (e->use_pdl ? 1 : 0) | ((count > 1 && e->chain_coop) ? 2 : 0);
   if (!conv_launch(L0.n_tile, L0.mt, L0.pair, taps, c, grid, L0.smem, st, launch_mode, &ce)) return fail(FLOPE_EINVAL, "no kernel instance for " + L0.name);
   if (ce != cudaSuccess) return fail(FLOPE_ECUDA, "launch of " + L0.name + ": " + cudaGetErrorString(ce));
+  ++e->launches;
+  return FLOPE_OK;
+}
+
+// layer1 .. layer4 as one launch (trunk_chain.cuh) when the plan has the shapes that kernel is instantiated for.
+bool trunk_eligible(const flope_engine* e) {
+  if (!e->use_trunk || !e->use_chain || !e->use_pair || e->chain_dynamic || e->chain_coop || e->chains.size() != kTrunkStages) return false;
+  static const int shape[kTrunkStages][2] = {{64, 4}, {128, 2}, {256, 1}, {256, 1}};
+  for (int s = 0; s < kTrunkStages; ++s) {
+    if (e->chains[s].size() != (size_t)kMaxChain) return false;
+    for (int li : e->chains[s]) {
+      const ConvLayer& L = e->layers[li];
+      if (!L.pair || L.pool || L.n_tile != shape[s][0] || L.mt != shape[s][1] || L.p.kc8 != 8 || L.p.b_resident) return false;
+    }
+    const ConvLayer& first = e->layers[e->chains[s][0]];
+    if (s > 0 && first.kind != K_CONV3_S2) return false;
+  }
+  return true;
+}
+
+int run_trunk(flope_engine* e, int n, cudaStream_t st) {
+  ProfScope ps(e, "conv:layer1-4 (one launch, 16 convs)", st);
+  TrunkParams tp;                                 // ~11 KB of kernel arguments
+  std::memset(&tp, 0, sizeof(tp));
+  size_t rings = 0;
+  long long items = 0;
+  int rc;
+  for (int s = 0; s < kTrunkStages; ++s) {
+    ConvLayer* Ls[kMaxChain];
+    for (int i = 0; i < kMaxChain; ++i) Ls[i] = &e->layers[e->chains[s][i]];
+    if ((rc = build_chain(e, Ls, kMaxChain, n, e->d_flags + s * e->flags_per_chain, tp.st[s]))) return rc;
+    tp.tile_pos[s] = Ls[0]->mt * 256;
+    // plan_conv's size = 1024 + its own bias block + rings; the kernel keeps one bias block of the largest stage
+    rings = std::max(rings, Ls[0]->smem - 1024 - (size_t)kMaxChain * Ls[0]->cout * sizeof(float));
+    items += (long long)tp.st[s].n_layers * tp.st[s].L[0].n_work;
+  }
+  const size_t smem = 1024 + (size_t)kMaxChain * 512 * sizeof(float) + rings;
+  if (smem > (size_t)kMaxSmem) return fail(FLOPE_EINVAL, "trunk launch does not fit in shared memory");
+  dim3 grid((unsigned)(2 * std::min<long long>(items, e->num_sms / 2)));
+  if (e->d_stamps && e->stamp_launch < kStampLaunches && grid.x <= 148) tp.stamps = e->d_stamps + (size_t)e->stamp_launch++ * 148 * kStampWords;
+  cudaError_t ce = launch_k(trunk_chain_kernel, grid, dim3(kConvThreads), smem, st, 2, e->use_pdl ? 1 : 0, tp);
+  if (ce != cudaSuccess) return fail(FLOPE_ECUDA, std::string("launch of the trunk chain: ") + cudaGetErrorString(ce));
   ++e->launches;
   return FLOPE_OK;
 }
@@ -604,6 +661,10 @@ int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
   // mode 2: the stem .. layer4 conv_igemm launches (the trunk) as they run in production - back to back, programmatic
   // dependent launch overlapping each prologue with its predecessor's tail - between ONE pair of events
   if (e->use_chain && e->d_flags) CUDA_TRY(cudaMemsetAsync(e->d_flags, 0, e->chains.size() * e->flags_per_chain * sizeof(uint32_t), st));
+  if (e->d_stamps) {
+    e->stamp_launch = 0;
+    CUDA_TRY(cudaMemsetAsync(e->d_stamps, 0, (size_t)kStampLaunches * 148 * kStampWords * sizeof(unsigned long long), st));
+  }
   std::unique_ptr<ProfScope> trunk(new ProfScope(e, "trunk", st, 2));
   if (e->fuse_pool) {
     ++li;
@@ -617,7 +678,10 @@ int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
     launch_k(maxpool3x3s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, 1, e->use_pdl, a.d, a.g, b.d, b.g, n);
     ++e->launches;
   }
-  if (e->use_chain && !e->chains.empty()) {
+  if (trunk_eligible(e)) {
+    if ((rc = run_trunk(e, n, st))) return rc;
+    li = e->layers.size() - 1;
+  } else if (e->use_chain && !e->chains.empty()) {
     // one launch per stage: its four convs as a layer-major stream of tiles, tile-level dependencies through flags
     for (size_t ci = 0; ci < e->chains.size(); ++ci) {
       ConvLayer* Ls[kMaxChain];
@@ -794,6 +858,7 @@ void flope_engine_destroy(flope_engine* e) {
   for (ConvLayer& L : e->layers) { cudaFree(L.d_w); cudaFree(L.d_bias); }
   cudaFree(e->stem_pool.d_w); cudaFree(e->stem_pool.d_bias);
   cudaFree(e->d_flags);
+  cudaFree(e->d_stamps);
   cudaFree(e->d_feat); cudaFree(e->d_wrot); cudaFree(e->d_brot); cudaFree(e->d_r9);
   delete e;
 }
@@ -1091,6 +1156,16 @@ int flope_debug_normalise_lut(float* d_out, void* stream) {
   return FLOPE_OK;
 }
 
+int flope_debug_timeline(flope_engine* e, unsigned long long* out, int max_launches) {
+  if (!e || !out) return fail(FLOPE_EINVAL, "null argument");
+  if (!e->d_stamps) return fail(FLOPE_EINVAL, "timeline is off: flope_debug_set(e, \"timeline\", 1) first");
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const int n = std::min(std::min(max_launches, e->stamp_launch), kStampLaunches);
+  CUDA_TRY(cudaMemcpy(out, e->d_stamps, (size_t)n * 148 * kStampWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return n;
+}
+
 int flope_debug_set(flope_engine* e, const char* key, int value) {
   if (!e || !key) return fail(FLOPE_EINVAL, "NULL argument");
   if (!std::strcmp(key, "use_graph")) { e->use_graph = value != 0; return FLOPE_OK; }
@@ -1100,6 +1175,13 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
     return FLOPE_OK;
   }
   if (!std::strcmp(key, "chain_coop")) { e->chain_coop = value != 0; drop_graphs(e); return FLOPE_OK; }
+  if (!std::strcmp(key, "timeline")) {
+    drop_graphs(e);
+    if (value && !e->d_stamps) CUDA_TRY(cudaMalloc(&e->d_stamps, (size_t)kStampLaunches * 148 * kStampWords * sizeof(unsigned long long)));
+    if (!value && e->d_stamps) { cudaFree(e->d_stamps); e->d_stamps = nullptr; }
+    return FLOPE_OK;
+  }
+  if (!std::strcmp(key, "trunk")) { e->use_trunk = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "chain_dynamic")) { e->chain_dynamic = value; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "chain")) { e->use_chain = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "pdl")) { e->use_pdl = value != 0; drop_graphs(e); return FLOPE_OK; }

@@ -159,11 +159,17 @@ int flope_debug_normalise_lut(float* d_out, void* stream);
  *   "chain_dynamic" 0/1  chains claim their work items in index order from an atomic counter instead of
  *                      round-robin by block index: safe under partial residency without a cooperative launch
  *                      (default 0: 3 % slower than the static deal on a single stream)
+ *   "timeline"    0/1  record per-CTA phase stamps in the conv kernels (default 0; read with flope_debug_timeline)
  *   "pair"        0/1  CTA-pair (tcgen05 cta_group::2) conv kernels instead of single-CTA ones (default 1)
  *   "small_tiles" 0/1  latency-oriented tiles when max_batch cannot fill the SMs (default 1)
  * "pair" and "small_tiles" change the packed-weight layout: call flope_engine_load_weights again afterwards.
  * Activation names for flope_debug_activation additionally include "x0" (the stem's space-to-depth input). */
 int flope_debug_set(flope_engine* e, const char* key, int value);
+/* After flope_debug_set(e, "timeline", 1): synchronise and copy the phase stamps of the conv_igemm launches of the
+ * last forward, [launch][148 CTAs][8] uint64 (%globaltimer ns at kernel entry, prologue done, dependency wait done, first
+ * operands landed, last MMA issued, first accumulator ready, last store issued, exit;
+ * zeros for CTAs a launch did not have).  Returns the number of launches copied (<= max_launches, <= 32). */
+int flope_debug_timeline(flope_engine* e, unsigned long long* out, int max_launches);
 
 #ifdef __cplusplus
 }

@@ -194,7 +194,7 @@ def test_graph_replay_equals_direct_launches(eng224):
 
 
 def test_chain_scheduling_modes_agree_bitwise(cuda_lib, net):
-    """Per-layer launches, stage chains with the static round-robin deal, and stage chains that claim their work
+    """Per-layer launches, layer1-4 as one launch, stage chains with the static round-robin deal, and stage chains that claim their work
     items from an atomic counter compute every tile with the same arithmetic: identical bits, single-CTA and pair
     kernels, also with two engines on two streams in flight (dynamic claiming is the mode that is safe there
     without a cooperative launch)."""
@@ -210,10 +210,12 @@ def test_chain_scheduling_modes_agree_bitwise(cuda_lib, net):
             e.debug_set("chain", 0)
             ref = e.posenet_forward(x).clone()
             e.debug_set("chain", 1)
-            for dyn in (0, 1):
+            for dyn, trunk in ((0, 1), (0, 0), (1, 0)):     # layer1-4 in one launch / a launch per stage / dynamic claims
                 e.debug_set("chain_dynamic", dyn)
+                e.debug_set("trunk", trunk)
                 for _ in range(3):                      # direct launches, graph capture, graph replay
-                    assert torch.equal(e.posenet_forward(x), ref), (pair, dyn)
+                    assert torch.equal(e.posenet_forward(x), ref), (pair, dyn, trunk)
+            e.debug_set("trunk", 1)
             for e in engs:
                 e.debug_set("chain_dynamic", 1)
             streams = [torch.cuda.Stream() for _ in engs]
