@@ -155,6 +155,8 @@ int flope_debug_normalise_lut(float* d_out, void* stream);
  *   "roi_strip"   even 2..128  output rows per CTA of the bilinear ROI kernel (default 14)
  *   "chain"       0/1  one persistent launch per ResNet stage (four convs, per-tile dependencies) instead of one
  *                      launch per layer (default 1; see the concurrency note at the top)
+ *   "trunk"       0/1  layer1..layer4 as ONE launch (trunk_chain_kernel) when the plan has its tile shapes (default 1;
+ *                      needs "chain" 1, "pair" 1, no "chain_coop"/"chain_dynamic"; same concurrency note)
  *   "chain_coop"  0/1  launch the chains cooperatively (default 0; required when engines share a device)
  *   "chain_dynamic" 0/1  chains claim their work items in index order from an atomic counter instead of
  *                      round-robin by block index: safe under partial residency without a cooperative launch
