@@ -19,7 +19,7 @@ SYMBOLS = [
     "flope_version", "flope_last_error", "flope_engine_create", "flope_engine_destroy",
     "flope_engine_load_weights", "flope_squarify_filter", "flope_roi_crop", "flope_posenet_forward",
     "flope_pose_head", "flope_nullify_yaw", "flope_infer_frames", "flope_engine_last_launches",
-    "flope_debug_activation", "flope_debug_normalise_lut", "flope_debug_set", "flope_debug_timeline",
+    "flope_debug_activation", "flope_debug_normalise_lut", "flope_debug_set", "flope_debug_timeline", "flope_ingest_crops",
     "flope_engine_profile", "flope_engine_profile_read", "flope_depth_values", "flope_yolo_mask",
 ]
 
@@ -51,6 +51,7 @@ def lib():
         L.flope_roi_crop.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.flope_posenet_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.flope_ingest_crops.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.flope_pose_head.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.flope_nullify_yaw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.flope_infer_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p,
@@ -195,6 +196,10 @@ class Engine:
         check(lib().flope_roi_crop(self._h, _ptr(frames), n_frames, H, W, frames.stride(0), _ptr(masks), _ptr(boxes5), n, S,
                                    interp, _ptr(out), out_fmt, _stream()))
         return out
+
+    def ingest_crops(self, x):
+        """Stage (n,3,S,S) float32 crops as the engine's stem input; posenet_forward(None, n) consumes them."""
+        check(lib().flope_ingest_crops(self._h, _ptr(x), x.shape[0], _stream()))
 
     def posenet_forward(self, x, n=None, out=None):
         """x: (n,3,S,S) float32 cuda tensor, or None to consume crops written by roi_crop(OUT_ENGINE)."""

@@ -978,6 +978,24 @@ int flope_roi_crop(flope_engine* e, const uint8_t* d_frames, int n_frames, int H
                  (cudaStream_t)stream);
 }
 
+int flope_ingest_crops(flope_engine* e, const float* d_in, int n, void* stream) {
+  if (!e || !d_in) return fail(FLOPE_EINVAL, "NULL argument");
+  if (n < 0 || n > e->max_batch) return fail(FLOPE_EINVAL, "bad n (0 .. max_batch)");
+  if (n == 0) return FLOPE_OK;
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const ActBuf& x0 = e->bufs[e->buf_x0];
+  const long long total = (long long)n * e->S * (e->S / 4);
+  e->launches = 0;
+  {
+    ProfScope ps(e, "ingest", st);
+    ingest_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, st>>>(d_in, n, e->S, x0.d, x0.g);
+    ++e->launches;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return FLOPE_OK;
+}
+
 int flope_posenet_forward(flope_engine* e, const float* d_in, int n, float* d_r9, void* stream) {
   if (!e || !d_r9) return fail(FLOPE_EINVAL, "NULL argument");
   if (!e->weights_loaded) return fail(FLOPE_ESTATE, "weights not loaded");

@@ -87,6 +87,13 @@ int flope_roi_crop(flope_engine* e, const uint8_t* d_frames, int n_frames, int H
  * flope_roi_crop(..., FLOPE_OUT_ENGINE) (then n <= max_batch).  d_r9: (n,9) float32. */
 int flope_posenet_forward(flope_engine* e, const float* d_in, int n, float* d_r9, void* stream);
 
+/* The first half of flope_posenet_forward on its own: convert (n,3,S,S) float32 NCHW crops (n <= max_batch) into the
+ * engine's stem input, so that flope_posenet_forward(e, NULL, n, ...) can follow later.  Lets a caller with two engines
+ * stage step i+1 on one of them (this call, or flope_roi_crop(..., FLOPE_OUT_ENGINE)) while the other runs step i's
+ * backbone - the staging kernels are small enough to share the SMs with the persistent conv kernels
+ * (flope_b200.pipeline.EnginePool(serial_backbones=True)). */
+int flope_ingest_crops(flope_engine* e, const float* d_in, int n, void* stream);
+
 /* Replaces procrustes_to_rotmat (sunflower/utils/conversion.py:54-58 -> roma.special_procrustes)
  * and, when d_R_yaw != NULL, nullify_yaw_batch (sunflower/utils/mvg.py:240-251).
  * d_r9: (n,9) f32.  d_R: (n,9) f32 row-major rotations (nullable).  d_R_yaw: (n,9) f64 (nullable). */

@@ -232,3 +232,26 @@ def test_chain_scheduling_modes_agree_bitwise(cuda_lib, net):
     finally:
         for e in engs:
             e.close()
+
+
+def test_staged_pool_matches_single_engine(cuda_lib, net):
+    """EnginePool(serial_backbones=True): staging (flope_ingest_crops) of step i+1 on one engine while the other runs
+    step i's backbone (layer1-4 as one launch on both) - same bits as one engine doing the steps in order."""
+    from flope_b200.pipeline import EnginePool
+    xs = [synth.mixed_crops(40, 224, seed=s).cuda() for s in (5, 6, 7)]
+    one = cuda_lib.Engine(0, max_batch=40, crop_hw=224)
+    pool = EnginePool("cuda:0", n_engines=2, max_batch=40, crop_hw=224, state_dict=net.state_dict(), serial_backbones=True)
+    try:
+        one.load_state_dict(net.state_dict())
+        refs = [one.posenet_forward(x).clone() for x in xs]
+        outs = [torch.empty((40, 9), device="cuda") for _ in range(9)]
+        for i in range(9):
+            pool.submit_staged(lambda e, k, i=i: e.ingest_crops(xs[i % 3]),
+                               lambda e, k, i=i: e.posenet_forward(None, n=40, out=outs[i]))
+        pool.join()
+        torch.cuda.synchronize()
+        for i in range(9):
+            assert torch.equal(outs[i], refs[i % 3]), i
+    finally:
+        pool.close()
+        one.close()
