@@ -144,7 +144,11 @@ cudaError_t conv_set_all_attrs() {
 #define X(N, M, K, P, R, T) if ((e = conv_set_attr<N, M, K, P, R, T>()) != cudaSuccess) return e;
   FOR_EACH_CONV_CFG(X)
 #undef X
-  return cudaFuncSetAttribute(trunk_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  if ((e = cudaFuncSetAttribute(trunk_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(trunk_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(trunk_chain_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(trunk_chain_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(trunk_chain_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
 }
 // returns false when no kernel instance matches; *err receives the launch status otherwise
 bool conv_launch(int n_tile, int mt, bool pair, int taps, const ConvChain& c, dim3 grid, size_t smem, cudaStream_t st, int pdl,
@@ -602,27 +606,43 @@ int run_convs(flope_engine* e, ConvLayer* const* Ls, int count, int n, cudaStrea
   return FLOPE_OK;
 }
 
-// layer1 .. layer4 as one launch (trunk_chain.cuh) when the plan has the shapes that kernel is instantiated for.
-bool trunk_eligible(const flope_engine* e) {
-  if (!e->use_trunk || !e->use_chain || !e->use_pair || e->chain_dynamic || e->chain_coop || e->chains.size() != kTrunkStages) return false;
+// Shared memory of the trunk launch: plan_conv's size of a stage = 1024 + its own bias block + rings; the trunk kernel
+// keeps one bias block of the largest stage (kMaxChain x 512 channels) in front of the largest rings.
+size_t trunk_smem(const flope_engine* e) {
+  size_t rings = 0;
+  for (const auto& ch : e->chains) {
+    const ConvLayer& L = e->layers[ch[0]];
+    rings = std::max(rings, L.smem - 1024 - (size_t)kMaxChain * L.cout * sizeof(float));
+  }
+  return 1024 + (size_t)kMaxChain * 512 * sizeof(float) + rings;
+}
+
+// layer1 .. layer4 as one launch (trunk_chain.cuh) when the plan has the shapes that kernel is instantiated for:
+// returns the mask of stages on latency tiles (64x1), or -1 when the trunk kernel does not apply.
+int trunk_shape_mask(const flope_engine* e) {
+  if (!e->use_trunk || !e->use_chain || !e->use_pair || e->chain_dynamic || e->chain_coop || e->chains.size() != kTrunkStages) return -1;
   static const int shape[kTrunkStages][2] = {{64, 4}, {128, 2}, {256, 1}, {256, 1}};
+  int mask = 0;
   for (int s = 0; s < kTrunkStages; ++s) {
-    if (e->chains[s].size() != (size_t)kMaxChain) return false;
+    if (e->chains[s].size() != (size_t)kMaxChain) return -1;
+    const ConvLayer& first = e->layers[e->chains[s][0]];
+    const bool small = first.n_tile == 64 && first.mt == 1;
+    if (small) mask |= 1 << s;
     for (int li : e->chains[s]) {
       const ConvLayer& L = e->layers[li];
-      if (!L.pair || L.pool || L.n_tile != shape[s][0] || L.mt != shape[s][1] || L.p.kc8 != 8 || L.p.b_resident) return false;
+      if (!L.pair || L.pool || L.p.kc8 != 8 || L.p.b_resident) return -1;
+      if (small ? (L.n_tile != 64 || L.mt != 1) : (L.n_tile != shape[s][0] || L.mt != shape[s][1])) return -1;
     }
-    const ConvLayer& first = e->layers[e->chains[s][0]];
-    if (s > 0 && first.kind != K_CONV3_S2) return false;
+    if (s > 0 && first.kind != K_CONV3_S2) return -1;
   }
-  return true;
+  if (trunk_smem(e) > (size_t)kMaxSmem) return -1;          // e.g. 512-pixel crops: the per-stage chains run instead
+  return (mask == 0 || mask == 8 || mask == 12 || mask == 14 || mask == 15) ? mask : -1;
 }
 
 int run_trunk(flope_engine* e, int n, cudaStream_t st) {
   ProfScope ps(e, "conv:layer1-4 (one launch, 16 convs)", st);
   TrunkParams tp;                                 // ~11 KB of kernel arguments
   std::memset(&tp, 0, sizeof(tp));
-  size_t rings = 0;
   long long items = 0;
   int rc;
   for (int s = 0; s < kTrunkStages; ++s) {
@@ -630,15 +650,20 @@ int run_trunk(flope_engine* e, int n, cudaStream_t st) {
     for (int i = 0; i < kMaxChain; ++i) Ls[i] = &e->layers[e->chains[s][i]];
     if ((rc = build_chain(e, Ls, kMaxChain, n, e->d_flags + s * e->flags_per_chain, tp.st[s]))) return rc;
     tp.tile_pos[s] = Ls[0]->mt * 256;
-    // plan_conv's size = 1024 + its own bias block + rings; the kernel keeps one bias block of the largest stage
-    rings = std::max(rings, Ls[0]->smem - 1024 - (size_t)kMaxChain * Ls[0]->cout * sizeof(float));
     items += (long long)tp.st[s].n_layers * tp.st[s].L[0].n_work;
   }
-  const size_t smem = 1024 + (size_t)kMaxChain * 512 * sizeof(float) + rings;
-  if (smem > (size_t)kMaxSmem) return fail(FLOPE_EINVAL, "trunk launch does not fit in shared memory");
+  const size_t smem = trunk_smem(e);
   dim3 grid((unsigned)(2 * std::min<long long>(items, e->num_sms / 2)));
   if (e->d_stamps && e->stamp_launch < kStampLaunches && grid.x <= 148) tp.stamps = e->d_stamps + (size_t)e->stamp_launch++ * 148 * kStampWords;
-  cudaError_t ce = launch_k(trunk_chain_kernel, grid, dim3(kConvThreads), smem, st, 2, e->use_pdl ? 1 : 0, tp);
+  cudaError_t ce = cudaErrorInvalidValue;
+  const int pdl = e->use_pdl ? 1 : 0;
+  switch (trunk_shape_mask(e)) {
+    case 0: ce = launch_k(trunk_chain_kernel<0>, grid, dim3(kConvThreads), smem, st, 2, pdl, tp); break;
+    case 8: ce = launch_k(trunk_chain_kernel<8>, grid, dim3(kConvThreads), smem, st, 2, pdl, tp); break;
+    case 12: ce = launch_k(trunk_chain_kernel<12>, grid, dim3(kConvThreads), smem, st, 2, pdl, tp); break;
+    case 14: ce = launch_k(trunk_chain_kernel<14>, grid, dim3(kConvThreads), smem, st, 2, pdl, tp); break;
+    case 15: ce = launch_k(trunk_chain_kernel<15>, grid, dim3(kConvThreads), smem, st, 2, pdl, tp); break;
+  }
   if (ce != cudaSuccess) return fail(FLOPE_ECUDA, std::string("launch of the trunk chain: ") + cudaGetErrorString(ce));
   ++e->launches;
   return FLOPE_OK;
@@ -678,7 +703,7 @@ int run_backbone_launches(flope_engine* e, int n, cudaStream_t st) {
     launch_k(maxpool3x3s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, 1, e->use_pdl, a.d, a.g, b.d, b.g, n);
     ++e->launches;
   }
-  if (trunk_eligible(e)) {
+  if (trunk_shape_mask(e) >= 0) {
     if ((rc = run_trunk(e, n, st))) return rc;
     li = e->layers.size() - 1;
   } else if (e->use_chain && !e->chains.empty()) {

@@ -11,8 +11,9 @@
 // that happens between stages:
 //   * work items of all stages are numbered stage-major, layer-major and dealt round-robin to the CTA pairs; every role
 //     (producer / MMA issuer or relay / epilogue warps) carries its own item counter across the stages;
-//   * the tile shape is a compile-time property (64x4, 128x2, 256x1 = N_TILE x MT sub-tiles), so each role calls one
-//     template instance per stage; all shapes use the same 2 x 256 TMEM columns;
+//   * the tile shape is a compile-time property (64x4, 128x2, 256x1 = N_TILE x MT sub-tiles; 64x1 latency tiles for
+//     stages that are too few items at a small max_batch), so each role calls one template instance per stage; all
+//     shapes use the same two 256-column TMEM accumulator stages;
 //   * the shared-memory rings are re-cut per stage (slot sizes differ).  The producer drains the old rings (waits for
 //     every slot's release) before its first copy into the new geometry - a bubble of one tile's MMAs per pair, at
 //     a moment that differs from pair to pair; barrier phases are tracked per slot (bit masks), because slot counts
@@ -58,12 +59,12 @@ struct TrunkStage {
   static constexpr int KP = 4, KC8 = 8;
   static constexpr int TM = MT * 128;
   static constexpr int NB_ROWS = N_TILE / 2;
-  static constexpr int ACC_COLS = pow2_at_least(N_TILE * MT);
+  static constexpr int ACC_COLS = 256;         // accumulator stage stride: the same for every stage shape
   static constexpr uint32_t IDESC = umma_idesc_bf16(256, N_TILE);
   static constexpr int NCHUNK = N_TILE / 32;
   static constexpr int TILE_POS = 2 * TM;
   static constexpr uint32_t b_tile_bytes = (uint32_t)KC8 * NB_ROWS * 16u;
-  static_assert(ACC_COLS == 256, "every stage uses the same two 256-column accumulator stages");
+  static_assert(N_TILE * MT <= ACC_COLS, "a tile's accumulators fit one 256-column stage");
 
   // ===================== TMA producer (warp 0 of both CTAs) =====================
   // prev: the previous stage (nullptr for the first), prev_tile_pos: positions per pair tile there
@@ -353,8 +354,21 @@ struct TrunkStage {
   }
 };
 
-// Stage shapes of ResNet-18 with the CTA-pair plan (engine.cu plan_conv): 64 channels -> 64x4, 128 -> 128x2, >= 256 -> 256x1.
+// Stage shapes of ResNet-18 with the CTA-pair plan (engine.cu plan_conv): 64 channels -> 64x4, 128 -> 128x2, >= 256 -> 256x1;
+// a stage whose layers would be too few items at the engine's max_batch runs on the latency tiles 64x1 instead
+// (bit s of SMALL; small batches switch the late stages first: 0, 8, 12, 14, 15 are the masks that occur).
+template <int S, bool SMALL> struct TrunkShape { using type = TrunkStage<64, 1>; };
+template <> struct TrunkShape<0, false> { using type = TrunkStage<64, 4>; };
+template <> struct TrunkShape<1, false> { using type = TrunkStage<128, 2>; };
+template <> struct TrunkShape<2, false> { using type = TrunkStage<256, 1>; };
+template <> struct TrunkShape<3, false> { using type = TrunkStage<256, 1>; };
+
+template <int SMALL>
 __global__ void __launch_bounds__(kConvThreads, 1) trunk_chain_kernel(const __grid_constant__ TrunkParams tp) {
+  using St0 = typename TrunkShape<0, (SMALL & 1) != 0>::type;
+  using St1 = typename TrunkShape<1, (SMALL & 2) != 0>::type;
+  using St2 = typename TrunkShape<2, (SMALL & 4) != 0>::type;
+  using St3 = typename TrunkShape<3, (SMALL & 8) != 0>::type;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   TrunkCtx c;
   c.a_full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -406,26 +420,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) trunk_chain_kernel(const __gr
   for (int s = 0; s < kTrunkStages; ++s) base[s + 1] = base[s] + tp.st[s].n_layers * tp.st[s].L[0].n_work;
   TrunkRole role;
   if (c.warp == 0) {
-    TrunkStage<64, 4>::producer(tp.st[0], nullptr, 0, base[0], c, role);
-    TrunkStage<128, 2>::producer(tp.st[1], &tp.st[0], tp.tile_pos[0], base[1], c, role);
-    TrunkStage<256, 1>::producer(tp.st[2], &tp.st[1], tp.tile_pos[1], base[2], c, role);
-    TrunkStage<256, 1>::producer(tp.st[3], &tp.st[2], tp.tile_pos[2], base[3], c, role);
+    St0::producer(tp.st[0], nullptr, 0, base[0], c, role);
+    St1::producer(tp.st[1], &tp.st[0], tp.tile_pos[0], base[1], c, role);
+    St2::producer(tp.st[2], &tp.st[1], tp.tile_pos[1], base[2], c, role);
+    St3::producer(tp.st[3], &tp.st[2], tp.tile_pos[2], base[3], c, role);
   } else if (c.warp == 1 && c.rank != 0) {
-    TrunkStage<64, 4>::relay(tp.st[0], base[0], c, role);
-    TrunkStage<128, 2>::relay(tp.st[1], base[1], c, role);
-    TrunkStage<256, 1>::relay(tp.st[2], base[2], c, role);
-    TrunkStage<256, 1>::relay(tp.st[3], base[3], c, role);
+    St0::relay(tp.st[0], base[0], c, role);
+    St1::relay(tp.st[1], base[1], c, role);
+    St2::relay(tp.st[2], base[2], c, role);
+    St3::relay(tp.st[3], base[3], c, role);
   } else if (c.warp == 1) {
-    TrunkStage<64, 4>::mma(tp.st[0], base[0], c, role);
-    TrunkStage<128, 2>::mma(tp.st[1], base[1], c, role);
-    TrunkStage<256, 1>::mma(tp.st[2], base[2], c, role);
-    TrunkStage<256, 1>::mma(tp.st[3], base[3], c, role);
+    St0::mma(tp.st[0], base[0], c, role);
+    St1::mma(tp.st[1], base[1], c, role);
+    St2::mma(tp.st[2], base[2], c, role);
+    St3::mma(tp.st[3], base[3], c, role);
     if (c.lane == 0) stamp(4);
   } else {
-    TrunkStage<64, 4>::epilogue(tp.st[0], base[0], c, role);
-    TrunkStage<128, 2>::epilogue(tp.st[1], base[1], c, role);
-    TrunkStage<256, 1>::epilogue(tp.st[2], base[2], c, role);
-    TrunkStage<256, 1>::epilogue(tp.st[3], base[3], c, role);
+    St0::epilogue(tp.st[0], base[0], c, role);
+    St1::epilogue(tp.st[1], base[1], c, role);
+    St2::epilogue(tp.st[2], base[2], c, role);
+    St3::epilogue(tp.st[3], base[3], c, role);
     if (threadIdx.x == 64) stamp(6);
   }
   tc_fence_before();

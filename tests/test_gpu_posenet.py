@@ -255,3 +255,25 @@ def test_staged_pool_matches_single_engine(cuda_lib, net):
     finally:
         pool.close()
         one.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_batch,n", [(8, 8), (8, 3), (32, 32), (64, 50), (120, 120)])
+def test_trunk_launch_small_batches_bitwise(cuda_lib, net, max_batch, n):
+    """Small engines put the late stages (or all) on latency tiles; layer1-4 as one launch must still equal the
+    per-stage chains and the per-layer launches bit for bit."""
+    x = synth.mixed_crops(n, 224, seed=max_batch + n).cuda()
+    e = cuda_lib.Engine(0, max_batch=max_batch, crop_hw=224)
+    try:
+        e.load_state_dict(net.state_dict())
+        outs = []
+        for chain, trunk in ((0, 0), (1, 0), (1, 1)):
+            e.debug_set("chain", chain)
+            e.debug_set("trunk", trunk)
+            for _ in range(2):
+                outs.append(e.posenet_forward(x).clone())
+        torch.cuda.synchronize()
+        for o in outs[1:]:
+            assert torch.equal(o, outs[0])
+    finally:
+        e.close()

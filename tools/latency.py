@@ -12,6 +12,8 @@ for S, interp, name in ((224, _lib.INTERP_LINEAR, "bilinear-224"), (512, _lib.IN
     sq, keep = _lib.squarify_filter(np.ascontiguousarray(det[0]), 1080, 1920)
     b5 = np.concatenate([np.zeros((len(sq), 1), np.int32), sq], 1)
     eng = _lib.Engine(0, max_batch=8, crop_hw=S)
+    for kv in filter(None, os.environ.get("FLOPE_SET", "").split(",")):
+        eng.debug_set(kv.split("=")[0], int(kv.split("=")[1]))
     eng.load_state_dict(synth.random_state_dict(0))
     hf, hm, hb = torch.from_numpy(frames).pin_memory(), torch.from_numpy(masks).pin_memory(), torch.from_numpy(b5).pin_memory()
     df, dm, db = hf.cuda(), hm.cuda(), hb.cuda()
