@@ -606,15 +606,11 @@ int run_convs(flope_engine* e, ConvLayer* const* Ls, int count, int n, cudaStrea
   return FLOPE_OK;
 }
 
-// Shared memory of the trunk launch: plan_conv's size of a stage = 1024 + its own bias block + rings; the trunk kernel
-// keeps one bias block of the largest stage (kMaxChain x 512 channels) in front of the largest rings.
+// Shared memory of the trunk launch: every stage is laid out exactly like its per-stage chain, so the largest plan.
 size_t trunk_smem(const flope_engine* e) {
-  size_t rings = 0;
-  for (const auto& ch : e->chains) {
-    const ConvLayer& L = e->layers[ch[0]];
-    rings = std::max(rings, L.smem - 1024 - (size_t)kMaxChain * L.cout * sizeof(float));
-  }
-  return 1024 + (size_t)kMaxChain * 512 * sizeof(float) + rings;
+  size_t m = 0;
+  for (const auto& ch : e->chains) m = std::max(m, e->layers[ch[0]].smem);
+  return m;
 }
 
 // layer1 .. layer4 as one launch (trunk_chain.cuh) when the plan has the shapes that kernel is instantiated for:
@@ -635,7 +631,6 @@ int trunk_shape_mask(const flope_engine* e) {
     }
     if (s > 0 && first.kind != K_CONV3_S2) return -1;
   }
-  if (trunk_smem(e) > (size_t)kMaxSmem) return -1;          // e.g. 512-pixel crops: the per-stage chains run instead
   return (mask == 0 || mask == 8 || mask == 12 || mask == 14 || mask == 15) ? mask : -1;
 }
 

@@ -22,7 +22,8 @@
 //     previous stage's parity-split output) waits for the previous stage's tiles that cover its halo rows: half-res
 //     rows h0..h1 of crop range n0..n1 <- full-res rows 2*h0 .. 2*h1+1, a contiguous tile range.  The 1x1 projection
 //     (folded into conv2 as extra K) reads positions its own conv1 neighbours already waited for;
-//   * the epilogue warps re-stage the stage's folded-BN biases between two named barriers of their own.
+//   * the epilogue warps re-stage the stage's folded-BN biases between two named barriers of their own; each stage's
+//     rings start right behind its own bias block.
 // Static dealing needs every CTA resident (grid <= SM count, one engine per device at a time) - the same condition as
 // the per-stage chains; engines that share a device keep per-layer launches (pipeline.EnginePool).
 #pragma once
@@ -40,7 +41,7 @@ struct TrunkParams {
 struct TrunkCtx {
   uint64_t *a_full, *a_empty, *b_full, *b_empty, *acc_full, *acc_empty;
   float* s_bias;
-  uint8_t* ring;                       // start of the operand rings (128-byte aligned)
+  uint8_t* smem;                       // start of dynamic shared memory (barriers, bias block, rings)
   uint32_t tmem_base;
   uint32_t rank;
   int lane, warp;
@@ -66,6 +67,14 @@ struct TrunkStage {
   static constexpr uint32_t b_tile_bytes = (uint32_t)KC8 * NB_ROWS * 16u;
   static_assert(N_TILE * MT <= ACC_COLS, "a tile's accumulators fit one 256-column stage");
 
+  // The rings of a stage start behind ITS bias block (kMaxChain x Cout floats), exactly as conv_igemm.cuh lays a chain
+  // out, so the launch needs no more shared memory than the largest stage.  A later stage's larger bias block grows
+  // into the previous stage's ring area - which is dead by then: the epilogue warps write it only after their last
+  // accumulator of the previous stage is complete, i.e. after every MMA that read those rings.
+  static __device__ __forceinline__ uint32_t ring_addr(const ConvChain& ch, const TrunkCtx& c) {
+    return (smem_u32(c.smem) + 512u + (uint32_t)(ch.n_layers * ch.L[0].Cout) * 4u + 127u) & ~127u;
+  }
+
   // ===================== TMA producer (warp 0 of both CTAs) =====================
   // prev: the previous stage (nullptr for the first), prev_tile_pos: positions per pair tile there
   static __device__ __forceinline__ void producer(const ConvChain& ch, const ConvChain* prev, int prev_tile_pos, int item_base,
@@ -75,7 +84,7 @@ struct TrunkStage {
     const uint32_t a_plane_bytes = (uint32_t)(TM + halo) * 16u;
     const uint32_t a_slot_bytes = a_plane_bytes * KC8;
     const uint32_t leader = elect_one() ? 1u : 0u;
-    const uint32_t a_ring_addr = smem_u32(c.ring);
+    const uint32_t a_ring_addr = ring_addr(ch, c);
     const uint32_t b_ring_addr = a_ring_addr + (uint32_t)p.n_a_slots * a_slot_bytes;
     const int total = ch.n_layers * p.n_work;
     const int img = p.Hp * p.Wp;
@@ -186,7 +195,7 @@ struct TrunkStage {
     const uint32_t a_slot_bytes = a_plane_bytes * KC8;
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-    const uint32_t a_ring_addr = smem_u32(c.ring);
+    const uint32_t a_ring_addr = ring_addr(ch, c);
     const uint32_t a_lo0 = ((a_plane_bytes >> 4) << 16) + (a_ring_addr >> 4) + (uint32_t)p.halo_before;
     const uint32_t b_lo0 = (((uint32_t)NB_ROWS * 16u >> 4) << 16) + ((a_ring_addr + (uint32_t)p.n_a_slots * a_slot_bytes) >> 4);
     const uint32_t a_kstep = 2u * (a_plane_bytes >> 4);
@@ -379,10 +388,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) trunk_chain_kernel(const __gr
   c.acc_empty = c.acc_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(c.acc_empty + 2);
   c.s_bias = reinterpret_cast<float*>(smem_raw + 512);
-  // the rings start behind the largest bias block of any stage (kMaxChain layers x 512 channels), as plan_conv sizes it
-  int bias_floats = 0;
-  for (int s = 0; s < kTrunkStages; ++s) bias_floats = max(bias_floats, tp.st[s].n_layers * tp.st[s].L[0].Cout);
-  c.ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 512 + (size_t)bias_floats * sizeof(float) + 127) & ~uintptr_t(127));
+  c.smem = smem_raw;
   c.warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   c.lane = threadIdx.x & 31;
   c.rank = cluster_ctarank();
