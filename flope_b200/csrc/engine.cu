@@ -133,7 +133,7 @@ cudaError_t conv_launch_t(const ConvChain& c, dim3 grid, size_t smem, cudaStream
 // tile, fused 3x3/s2 max-pool epilogue (stem), CTA-pair (cta_group::2) kernel, tap issue order (16 = stem rows, 0 = tables)
 #define FOR_EACH_CONV_CFG(X)                                                                                   \
   /* single-CTA */                                                                                             \
-  X(64, 4, 4, false, false, 0) X(128, 2, 4, false, false, 0)                                                   \
+  X(64, 4, 4, false, false, 0) X(128, 2, 4, false, false, 0) X(64, 1, 4, false, false, 0)                                                   \
   X(64, 4, 1, false, false, 16) X(64, 4, 1, true, false, 16)                                                   \
   /* CTA pair */                                                                                               \
   X(64, 4, 4, false, true, 0) X(128, 2, 4, false, true, 0) X(256, 1, 4, false, true, 0) X(64, 1, 4, false, true, 0) \
@@ -178,6 +178,7 @@ struct flope_engine {
   bool chain_coop = false;                       // launch chains cooperatively (gang-scheduled): needed when several engines share a device
   unsigned long long* d_stamps = nullptr;        // phase stamps of the conv launches of one forward ("timeline" debug option)
   int stamp_launch = 0;
+  bool fc_small = true;                          // fc on 128-row x 64-channel single-CTA tiles
   bool use_trunk = true;                         // layer1..layer4 as one launch when the plan allows (trunk_chain.cuh)
   int chain_dynamic = 0;                     // chains claim work items from an atomic counter (safe under partial residency)
   bool use_chain = true;                         // one persistent launch per ResNet stage (four convs) with per-tile completion flags
@@ -371,6 +372,11 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
   L.n_tile = L.cout >= 128 ? 128 : 64;
   if (L.pair && L.cout >= 256) L.n_tile = 256; // M = 256 x N = 256 MMAs: 8 KB of operand reads per SM per 128 tensor cycles
   L.mt = 256 / L.n_tile;                       // 2 stages x 256 columns = all 512 TMEM columns
+  if (L.kind == K_FC && e->fc_small) {
+    // fc: M = crops only.  With 256 x 128 tiles a 256-crop batch is 16 CTAs that each stream 384 KB of operands and
+    // store a 128 KB fp32 tile (17 us, a third of it epilogue); 128 x 64 tiles make it 64 short CTAs.
+    L.n_tile = 64; L.mt = 1;
+  }
   if (L.pair && !L.pool && L.kind != K_STEM && e->small_tiles) {
     // small batches (streaming: a handful of flowers per frame): with the throughput tiles a layer is a few work
     // items whose serial MMA chain (up to 288 K-steps at N = 256) is the whole latency.  128-position x 64-channel
@@ -1223,8 +1229,8 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
   if (!std::strcmp(key, "chain_dynamic")) { e->chain_dynamic = value; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "chain")) { e->use_chain = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "pdl")) { e->use_pdl = value != 0; drop_graphs(e); return FLOPE_OK; }
-  if (!std::strcmp(key, "pair") || !std::strcmp(key, "small_tiles")) {   // re-plans every layer; the packed weights depend on it: reload them
-    if (key[0] == 'p') e->use_pair = value != 0; else e->small_tiles = value != 0;
+  if (!std::strcmp(key, "pair") || !std::strcmp(key, "small_tiles") || !std::strcmp(key, "fc_small")) {   // re-plans every layer; the packed weights depend on it: reload them
+    if (key[0] == 'p') e->use_pair = value != 0; else if (key[0] == 's') e->small_tiles = value != 0; else e->fc_small = value != 0;
     drop_graphs(e);
     e->weights_loaded = false;
     for (ConvLayer& L : e->layers) { int rc = plan_conv(e, L); if (rc) return rc; }

@@ -171,7 +171,8 @@ int flope_debug_normalise_lut(float* d_out, void* stream);
  *   "timeline"    0/1  record per-CTA phase stamps in the conv kernels (default 0; read with flope_debug_timeline)
  *   "pair"        0/1  CTA-pair (tcgen05 cta_group::2) conv kernels instead of single-CTA ones (default 1)
  *   "small_tiles" 0/1  latency-oriented tiles when max_batch cannot fill the SMs (default 1)
- * "pair" and "small_tiles" change the packed-weight layout: call flope_engine_load_weights again afterwards.
+ *   "fc_small"    0/1  fc GEMM on 128-crop x 64-channel single-CTA tiles instead of 256 x 128 (default 1)
+ * "pair", "small_tiles" and "fc_small" change the packed-weight layout: call flope_engine_load_weights again afterwards.
  * Activation names for flope_debug_activation additionally include "x0" (the stem's space-to-depth input). */
 int flope_debug_set(flope_engine* e, const char* key, int value);
 /* After flope_debug_set(e, "timeline", 1): synchronise and copy the phase stamps of the conv_igemm launches of the
