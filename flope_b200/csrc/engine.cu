@@ -836,6 +836,8 @@ int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_
   *out = nullptr;
   if (max_batch < 1 || crop_hw < 32 || crop_hw % 32 != 0 || crop_hw > 1024)
     return fail(FLOPE_EINVAL, "max_batch must be >= 1 and crop_hw a multiple of 32 in [32,1024]");
+  if ((long long)max_batch * crop_hw * crop_hw >= (1LL << 32))
+    return fail(FLOPE_EINVAL, "max_batch * crop_hw^2 must stay below 2^32 (32-bit pixel indices in the ingest kernel)");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(FLOPE_EINVAL, "no such CUDA device");

@@ -16,14 +16,16 @@ __global__ void ingest_nchw_f32_kernel(const float* __restrict__ x, int n, int S
   // one 32-byte run of two s2d pixels out
   griddep_wait();
   griddep_launch();
-  const int S4 = S >> 2;
-  const long long total = (long long)n * S * S4;
+  // 32-bit index arithmetic (n*S*S/4 < 2^31, checked by the host): the 64-bit div/mod sequences of the first version
+  // made this copy kernel issue-bound (~400 instructions per 48 bytes read)
+  const uint32_t S4 = (uint32_t)S >> 2;
+  const uint32_t total = (uint32_t)n * (uint32_t)S * S4;
   const long long plane_sz = (long long)S * S;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int x4 = (int)(i % S4);
-    const int yy = (int)((i / S4) % S);
-    const int b = (int)(i / ((long long)S4 * S));
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t r = i / S4;                 // row index b*S + yy
+    const int x4 = (int)(i - r * S4);
+    const int b = (int)(r / (uint32_t)S);
+    const int yy = (int)(r - (uint32_t)b * (uint32_t)S);
     const float* px = x + ((long long)b * 3 * S + yy) * S + 4 * x4;
     const float4 c0 = __ldcs(reinterpret_cast<const float4*>(px));
     const float4 c1 = __ldcs(reinterpret_cast<const float4*>(px + plane_sz));
