@@ -10,7 +10,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--crops", type=int, default=1_000_000)
 ap.add_argument("--micro", type=int, default=2048)
 ap.add_argument("--size", type=int, default=224)
-ap.add_argument("--inflight", type=int, default=2, help="micro-batches in flight per GPU (engines / streams)")
+ap.add_argument("--inflight", type=int, default=1, help="micro-batches in flight per GPU (engines / streams); 1 = one engine with layer1-4 as one launch, the fastest mode")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
