@@ -153,6 +153,11 @@ __global__ void __launch_bounds__(kHeadThreads) pose_head_kernel(const float* __
 #pragma unroll
     for (int j = 0; j < 9; ++j) r9[j] = r9_in[(size_t)crop * 9 + j];
   }
+  if (!R_in && !R_out && !Ryaw_out) {           // fc_rot only (flope_posenet_forward): no projection wanted
+    if (r9_out)
+      for (int j = 0; j < 9; ++j) r9_out[(size_t)crop * 9 + j] = r9[j];
+    return;
+  }
   double R[3][3];
   if (R_in) {                                   // yaw-only mode (mvg.nullify_yaw_batch mirror)
     for (int j = 0; j < 9; ++j) R[j / 3][j % 3] = (double)R_in[(size_t)crop * 9 + j];
