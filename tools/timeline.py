@@ -12,9 +12,10 @@ are involved):
   first     -> first operands in shared memory (MMA warp's first full barrier)
   main      -> last MMA issued
   tail      last MMA issued -> last epilogue store issued
-  exit      -> CTA exit
-  life      CTA entry -> exit
-  idle      SM-time of the launch not covered by a CTA's life: sum over CTAs of (span - life) / CTAs
+  life      CTA entry -> its last epilogue store
+  idle      SM-time of the launch not covered by a CTA's life: mean over CTAs of (span - life)
+(the stamp after the kernel's final barrier is not used for timing: ptxas schedules its timer read before the barrier.
+ trunk_chain_kernel records no first-operand / first-accumulator stamps: nan in `first` and `main`.)
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -38,22 +39,21 @@ for _ in range(2):
 torch.cuda.synchronize()
 t = eng.timeline().astype(np.int64)
 print(f"{B} crops of {S}x{S}; {len(t)} conv launches")
-print(f"{'launch':>6} {'CTAs':>5} {'span':>8} {'gap':>7} {'skew':>6} {'prolog':>7} {'depwait':>8} {'first':>6} {'main':>8} {'tail':>6} {'exit':>6} {'life':>7} {'idle':>6}")
+print(f"{'launch':>6} {'CTAs':>5} {'span':>8} {'gap':>7} {'skew':>6} {'prolog':>7} {'depwait':>8} {'first':>6} {'main':>8} {'tail':>6} {'life':>7} {'idle':>6}")
 prev_end = None
 for i, L in enumerate(t):
     L = L[L[:, 0] != 0]
     if not len(L):
         continue
-    lead = L[:, 3] != 0
 
-    def c(a, b):
-        rows = lead if (a in (3, 4) or b in (3, 4)) else np.ones(len(L), bool)
-        return float(np.median((L[:, b] - L[:, a])[rows])) / 1e3
-    start, end = L[:, 0].min(), L[:, 7].max()
+    def c(a, b):                         # CTAs that recorded both stamps (the MMA warp's exist in the leader CTAs only)
+        rows = (L[:, a] != 0) & (L[:, b] != 0)
+        return float(np.median((L[:, b] - L[:, a])[rows])) / 1e3 if rows.any() else float("nan")
+    start, end = L[:, 0].min(), max(L[:, 6].max(), L[:, 7].max())
     gap = (start - prev_end) / 1e3 if prev_end is not None else float("nan")
-    life = L[:, 7] - L[:, 0]
+    life = L[:, 6] - L[:, 0]
     print(f"{i:>6} {len(L):>5} {(end-start)/1e3:>8.1f} {gap:>7.1f} {(L[:,0].max()-start)/1e3:>6.1f} {c(0,1):>7.2f} {c(1,2):>8.2f} "
-          f"{c(2,3):>6.2f} {c(3,4):>8.1f} {c(4,6):>6.2f} {c(6,7):>6.2f} {float(np.median(life))/1e3:>7.1f} {float(((end-start)-life).mean())/1e3:>6.1f}")
+          f"{c(2,3):>6.2f} {c(3,4):>8.1f} {c(4,6):>6.2f} {float(np.median(life))/1e3:>7.1f} {float(((end-start)-life).mean())/1e3:>6.1f}")
     prev_end = end
 raw = os.environ.get("TIMELINE_RAW")
 if raw is not None:                      # stamps of the first CTAs of one launch, ns relative to the launch's first entry
