@@ -167,7 +167,8 @@ int flope_debug_normalise_lut(float* d_out, void* stream);
  *   "chain_coop"  0/1  launch the chains cooperatively (default 0; required when engines share a device)
  *   "chain_dynamic" 0/1  chains claim their work items in index order from an atomic counter instead of
  *                      round-robin by block index: safe under partial residency without a cooperative launch
- *                      (default 0: 3 % slower than the static deal on a single stream)
+ *                      (default 0: 3 % slower than the static deal on a single stream; 2 = the static deal routed
+ *                      through the same item queue, for diagnosis)
  *   "timeline"    0/1  record per-CTA phase stamps in the conv kernels (default 0; read with flope_debug_timeline)
  *   "pair"        0/1  CTA-pair (tcgen05 cta_group::2) conv kernels instead of single-CTA ones (default 1)
  *   "small_tiles" 0/1  latency-oriented tiles when max_batch cannot fill the SMs (default 1)
