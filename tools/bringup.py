@@ -1,7 +1,6 @@
 """GPU bring-up: per-layer comparison of the engine against the CPU oracle (run under gpurun)."""
 import argparse
 import sys
-import time
 import os
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

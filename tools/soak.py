@@ -3,7 +3,7 @@ engines in flight, every result compared bit for bit with the first one.  Prints
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from flope_b200 import _lib, synth
+from flope_b200 import synth
 from flope_b200.pipeline import EnginePool
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5000

@@ -1,6 +1,6 @@
 """BASELINE configs[3]: N synthetic crops batch-sharded across the ranks (torchrun), micro-batches through the
 engine, one final all_gather of the rotations.  Prints crops/s (max over ranks) on rank 0."""
-import argparse, json, os, sys, time
+import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
