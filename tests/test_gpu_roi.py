@@ -85,3 +85,83 @@ def test_engine_format_equals_f32_path(cuda_lib):
     torch.cuda.synchronize()
     assert torch.equal(a, b)
     e.close()
+
+
+def _b5(boxes, frame=0):
+    return torch.from_numpy(np.concatenate([np.full((len(boxes), 1), frame, np.int32), np.asarray(boxes, np.int32)], 1)).cuda()
+
+
+@pytest.mark.parametrize("interp,size", [(R.LANCZOS4, 512), (R.BILINEAR, 224), (R.LANCZOS4, 224), (R.BILINEAR, 512)])
+def test_staged_kernels_match_generic_and_arithmetic_modes(cuda_lib, interp, size):
+    """The staged kernels (TMA-staged rows, DP2A taps), their table-free normalise variant and the generic
+    one-thread-per-column kernel are three implementations of the same integer arithmetic: bitwise equal."""
+    rng = np.random.default_rng(21)
+    frame, mask = _frame(rng)
+    fr, mk, b5 = torch.from_numpy(frame).cuda()[None], torch.from_numpy(mask).cuda()[None], _b5(_boxes())
+    e = cuda_lib.Engine(0, max_batch=16, crop_hw=size)
+    outs = []
+    for staged, lut in ((1, 1), (1, 0), (0, 1)):
+        e.debug_set("roi_staged", staged); e.debug_set("roi_lut", lut)
+        outs.append(e.roi_crop(fr, mk, b5, size, interp).clone())
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    e.close()
+
+
+def test_engine_format_staged_equals_generic(cuda_lib):
+    """bf16 stem-input crops of the staged kernels (both normalise variants) vs the generic kernel: identical PoseNet outputs."""
+    from oracle import posenet as onet
+    net = onet.build(0)
+    e = cuda_lib.Engine(0, max_batch=16, crop_hw=224)
+    e.load_state_dict(net.state_dict())
+    rng = np.random.default_rng(22)
+    frame, mask = _frame(rng)
+    fr, mk, b5 = torch.from_numpy(frame).cuda()[None], torch.from_numpy(mask).cuda()[None], _b5(_boxes())
+    for interp in (R.BILINEAR, R.LANCZOS4):
+        outs = []
+        for staged, lut in ((1, 1), (1, 0), (0, 1)):
+            e.debug_set("roi_staged", staged); e.debug_set("roi_lut", lut)
+            e.roi_crop(fr, mk, b5, 224, interp, out_fmt=cuda_lib.OUT_ENGINE)
+            outs.append(e.posenet_forward(None, n=len(b5)).clone())
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), interp
+    e.close()
+
+
+@pytest.mark.parametrize("interp", [R.BILINEAR, R.LANCZOS4])
+def test_roi_frame_width_not_multiple_of_4_takes_generic_path(cuda_lib, eng, interp):
+    rng = np.random.default_rng(23)
+    frame, mask = _frame(rng, H=241, W=322)
+    boxes = np.array([[0, 0, 241, 241], [81, 0, 322, 241], [13, 17, 150, 154], [300, 200, 322, 222]], np.int32)
+    want = R.crop_batch_reference(frame, mask, boxes, size=224, interp=interp)
+    got = eng.roi_crop(torch.from_numpy(frame).cuda()[None], torch.from_numpy(mask).cuda()[None], _b5(boxes), 224, interp)
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("interp,size", [(R.BILINEAR, 224), (R.LANCZOS4, 512)])
+def test_roi_1080p_last_frames_of_64(cuda_lib, interp, size):
+    """BASELINE configs[2] geometry: 64 x 1080p frames (398 MB: byte offsets beyond 2^31), the configs[2] box
+    distribution; boxes taken from the last frames, whose-frame boxes and boxes touching the last row included."""
+    from flope_b200 import synth
+    frames, masks, det = synth.frames_and_boxes(3, 32, seed=13, with_mask=True)       # content of frames 61..63
+    big = torch.zeros((64, 1080, 1920, 3), dtype=torch.uint8, device="cuda")
+    bigm = torch.zeros((64, 1080, 1920), dtype=torch.uint8, device="cuda")
+    big[61:] = torch.from_numpy(frames).cuda()
+    bigm[61:] = torch.from_numpy(masks).cuda()
+    rows = []
+    for f in range(3):
+        sq, _ = cuda_lib.squarify_filter(np.ascontiguousarray(det[f]), 1080, 1920)
+        sel = sq[:10 if size == 224 else 3]
+        extra = np.array([[840, 0, 1920, 1080], [0, 1000, 80, 1080], [1900, 1060, 1920, 1080]], np.int32)
+        for bb in np.concatenate([sel, extra]):
+            rows.append([61 + f, *bb])
+    rows = np.array(rows, np.int32)
+    e = cuda_lib.Engine(0, max_batch=8, crop_hw=size)
+    got = e.roi_crop(big, bigm, torch.from_numpy(rows).cuda(), size, interp)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    for i, (f, *bb) in enumerate(rows):
+        want = R.crop_batch_reference(frames[f - 61], masks[f - 61], [bb], size=size, interp=interp)[0]
+        assert np.array_equal(got[i], want), (i, f, bb)
+    e.close()

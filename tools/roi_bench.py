@@ -1,11 +1,16 @@
-"""ROI kernel throughput on the frame configuration (BASELINE configs[2]): 64 x 1080p frames, 32 boxes each."""
+"""ROI kernel throughput on the frame configuration (BASELINE configs[2]): 1080p frames, 32 boxes each.
+
+usage: python tools/roi_bench.py [n_frames] [quick]
+Prints, per kernel variant, the time per launch (CUDA events, L2 flushed between launches), crops/s and the
+algorithmic HBM bandwidth (source box + mask + output bytes) against the measured peak."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from flope_b200 import _lib, synth
 
-n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+quick = len(sys.argv) > 2
 frames, masks, det = synth.frames_and_boxes(n_frames, 32, with_mask=True)
 b5 = []
 for f in range(n_frames):
@@ -30,22 +35,44 @@ def timeit(fn, reps=10):
     return float(np.median(ts))
 
 
+def report(tag, ms, byts, nn):
+    print(f"{tag}: {nn} crops {ms*1e3:.1f} us  {nn/ms*1e3:.0f} crops/s  {byts/ms/1e6:.0f} GB/s = "
+          f"{byts/ms/1e6/peak*100:.1f}% of measured HBM peak ({byts/nn:.0f} B/crop)", flush=True)
+
+
 eng = _lib.Engine(0, max_batch=n, crop_hw=224)
-for strip, mask_on in ((14, True), (14, False), (8, True), (8, False), (4, True), (28, True)):
-    eng.debug_set("roi_strip", strip)
-    print(f"{strip}-row strips", end=": ")
-    m = mk if mask_on else None
-    ms = timeit(lambda: eng.roi_crop(fr, m, bx, 224, _lib.INTERP_LINEAR, out_fmt=_lib.OUT_ENGINE))
-    byts = float((3 * side ** 2 + (side ** 2 if mask_on else 0) + 301056 + 20).sum())
-    print(f"bilinear->224 bf16 engine fmt mask={mask_on}: {n} crops {ms*1e3:.1f} us  {n/ms*1e3:.0f} crops/s  "
-          f"{byts/ms/1e6:.0f} GB/s = {byts/ms/1e6/peak*100:.1f}% of measured HBM peak ({byts/n:.0f} B/crop)")
+by_m = float((4 * side ** 2 + 301056 + 20).sum())
+by_n = float((3 * side ** 2 + 301056 + 20).sum())
+eng.debug_set("roi_staged", 0)
+ms = timeit(lambda: eng.roi_crop(fr, mk, bx, 224, _lib.INTERP_LINEAR, out_fmt=_lib.OUT_ENGINE))
+report("generic  bilinear->224 bf16 engine mask=1", ms, by_m, n)
+eng.debug_set("roi_staged", 1)
+cfgs = [(32, 2, 36, 1)] if quick else [(32, 2, 36, 1), (32, 2, 36, 0), (16, 2, 24, 1), (64, 2, 48, 1), (32, 1, 36, 1),
+                                       (16, 1, 24, 1), (64, 2, 48, 0), (28, 2, 36, 1), (56, 2, 48, 1)]
+for strip, sub, kb, lut in cfgs:
+    eng.debug_set("roi_strip", strip); eng.debug_set("roi_sub", sub); eng.debug_set("roi_data_kb", kb); eng.debug_set("roi_lut", lut)
+    for mask_on in (True, False):
+        m = mk if mask_on else None
+        ms = timeit(lambda: eng.roi_crop(fr, m, bx, 224, _lib.INTERP_LINEAR, out_fmt=_lib.OUT_ENGINE))
+        report(f"staged strip={strip} sub={sub} kb={kb} lut={lut} bilinear->224 bf16 engine mask={int(mask_on)}", ms,
+               by_m if mask_on else by_n, n)
 eng.close()
-nb = min(n, 512)
+
+nb = min(n, 256)
 eng = _lib.Engine(0, max_batch=8, crop_hw=512)
 out = torch.empty((nb, 3, 512, 512), device="cuda")
+s = side[:nb]
+byts = float((4 * s ** 2 + 3145728 + 20).sum())
+eng.debug_set("roi_staged", 0)
 for interp, name in ((_lib.INTERP_LANCZOS4, "lanczos4"), (_lib.INTERP_LINEAR, "bilinear")):
     ms = timeit(lambda: eng.roi_crop(fr, mk, bx[:nb], 512, interp, out=out), reps=5)
-    s = side[:nb]
-    byts = float((4 * s ** 2 + 3145728 + 20).sum())
-    print(f"{name}->512 f32 NCHW (reference layout) mask=True: {nb} crops {ms*1e3:.1f} us  {nb/ms*1e3:.0f} crops/s  "
-          f"{byts/ms/1e6:.0f} GB/s = {byts/ms/1e6/peak*100:.1f}% of measured HBM peak")
+    report(f"generic  {name}->512 f32 NCHW mask=1", ms, byts, nb)
+eng.debug_set("roi_staged", 1)
+for strip8, kb, lut in ([(128, 36, 1)] if quick else [(128, 36, 1), (128, 36, 0), (64, 36, 1), (128, 64, 1), (64, 24, 0)]):
+    eng.debug_set("roi_strip8", strip8); eng.debug_set("roi_data_kb", kb); eng.debug_set("roi_lut", lut)
+    ms = timeit(lambda: eng.roi_crop(fr, mk, bx[:nb], 512, _lib.INTERP_LANCZOS4, out=out), reps=5)
+    report(f"staged strip8={strip8} kb={kb} lut={lut} lanczos4->512 f32 NCHW mask=1", ms, byts, nb)
+eng.debug_set("roi_strip", 32); eng.debug_set("roi_data_kb", 36); eng.debug_set("roi_lut", 1)
+ms = timeit(lambda: eng.roi_crop(fr, mk, bx[:nb], 512, _lib.INTERP_LINEAR, out=out), reps=5)
+report("staged bilinear->512 f32 NCHW mask=1", ms, byts, nb)
+eng.close()
