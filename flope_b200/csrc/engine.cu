@@ -24,6 +24,7 @@
 #include "pose_head.cuh"
 #include "trunk_chain.cuh"
 #include "roi_crop.cuh"
+#include "roi_stream.cuh"
 
 using namespace flope;
 
@@ -174,6 +175,12 @@ struct flope_engine {
   std::map<std::string, int> act_names;          // debug name -> buffer index
   std::vector<ConvLayer> layers;
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
+  int roi_stream = 1;                            // streaming ROI kernels (roi3_kernel, roi_stream.cuh): the production path
+  int roi_item_rows = 28;                        // output rows per work item of the streaming bilinear kernel
+  int roi_item_rows8 = 32;                       // same for the streaming Lanczos4 kernel
+  int roi_stage_kb = 10;                         // bytes per ring stage of the streaming kernels
+  int roi_stages = 3;                            // ring depth
+  int roi_ctas_per_sm = 0;                       // 0 = as many as fit
   bool roi_staged = true;                        // staged ROI kernels (roi2_kernel); 0 = generic one-thread-per-column kernel
   int roi_strip = 32;                            // output rows per CTA of the staged bilinear ROI kernel
   int roi_sub = 2;                               // sub-strips per CTA of the staged bilinear ROI kernel
@@ -800,6 +807,29 @@ cudaError_t roi2_launch(const RoiParams& rp, dim3 grid, int block, size_t smem, 
   return cudaGetLastError();
 }
 
+// streaming ROI kernels (roi_stream.cuh): persistent grid, CTAs per SM from the occupancy calculator
+template <int TAPS, bool HAS_MASK, int FMT, int NCOL>
+cudaError_t roi3_launch(const Roi3Params& rp, int num_sms, int ctas_per_sm, int block, size_t smem, cudaStream_t st) {
+  static int occ[64] = {};                        // per device: opt in to > 48 KB of dynamic shared memory once
+  static size_t occ_smem[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!occ[dev] || occ_smem[dev] != smem) {
+    cudaError_t ce = cudaFuncSetAttribute(roi3_kernel<TAPS, HAS_MASK, FMT, NCOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (ce != cudaSuccess) return ce;
+    int n = 0;
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, roi3_kernel<TAPS, HAS_MASK, FMT, NCOL>, block, smem);
+    if (ce != cudaSuccess) return ce;
+    if (n < 1) return cudaErrorLaunchOutOfResources;
+    occ[dev] = n; occ_smem[dev] = smem;
+  }
+  const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, occ[dev]) : occ[dev];
+  const int grid = std::max(1, std::min(rp.n_items, num_sms * per_sm));
+  roi3_kernel<TAPS, HAS_MASK, FMT, NCOL><<<grid, block, smem, st>>>(rp);
+  return cudaGetLastError();
+}
+
 int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W, int64_t frame_stride,
             const uint8_t* d_masks, const int32_t* d_boxes, int n, int S, int interp, void* d_out, int out_fmt,
             cudaStream_t st) {
@@ -815,6 +845,39 @@ int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W
   const bool has_mask = d_masks != nullptr;
   const bool lanczos = interp == FLOPE_INTERP_LANCZOS4;
   ProfScope ps(e, lanczos ? "roi_crop:lanczos4" : "roi_crop:linear", st);
+  // ---- streaming kernels: 16-byte phase of a row segment independent of the row, one or two columns per thread ----
+  if (e->roi_stream && !lanczos && W % 16 == 0 && S <= 512 && S % (S <= 224 ? 32 : 64) == 0 && n_frames >= 1 && n >= 1 &&
+      (out_fmt != FLOPE_OUT_ENGINE || rp.g.plane * 16 < (1LL << 31))) {
+    Roi3Params q{};
+    q.frames = d_frames; q.frame_stride = frame_stride; q.masks = d_masks; q.mask_stride = (long long)H * W; q.W = W;
+    q.boxes = d_boxes; q.n = n; q.S = S; q.out_fmt = out_fmt; q.out = rp.out; q.g = rp.g;
+    q.rows_per_item = std::max(1, std::min(std::min(kR3MaxItemRows, S), lanczos ? e->roi_item_rows8 : e->roi_item_rows));
+    q.items_per_crop = (S + q.rows_per_item - 1) / q.rows_per_item;
+    q.n_items = n * q.items_per_crop;
+    const int side = std::min(H, W);                 // a square in-frame box is at most this wide
+    const int max_pitch = ((15 + 3 * side + 15) & ~15) + ((15 + side + 15) & ~15);
+    q.stage_bytes = (std::max(e->roi_stage_kb * 1024, 2 * max_pitch) + 127) & ~127;
+    q.n_stages = std::max(2, std::min(kR3MaxStages, e->roi_stages));
+    q.xtab_slot = S * 16;
+    q.ring_off = (kR3Xtab + 2 * q.xtab_slot + 127) & ~127;
+    const size_t smem = (size_t)q.ring_off + (size_t)q.n_stages * q.stage_bytes + kR3RingTail;
+    if (smem <= (size_t)kMaxSmem) {
+      const int ncol = S <= 224 ? 1 : 2;
+      const int block = 32 * (S / ncol / 32 + 1);
+      const int key = (ncol == 2 ? 4 : 0) | (has_mask ? 2 : 0) | (out_fmt == FLOPE_OUT_ENGINE ? 1 : 0);
+      cudaError_t ce;
+#define ROI3_CASE(K, M, F, C) case K: ce = roi3_launch<2, M, F, C>(q, e->num_sms, e->roi_ctas_per_sm, block, smem, st); break;
+      switch (key) {
+        ROI3_CASE(0, false, 0, 1) ROI3_CASE(1, false, 1, 1) ROI3_CASE(2, true, 0, 1) ROI3_CASE(3, true, 1, 1)
+        ROI3_CASE(4, false, 0, 2) ROI3_CASE(5, false, 1, 2) ROI3_CASE(6, true, 0, 2)
+        default: ce = roi3_launch<2, true, 1, 2>(q, e->num_sms, e->roi_ctas_per_sm, block, smem, st); break;
+      }
+#undef ROI3_CASE
+      if (ce != cudaSuccess) return fail(FLOPE_ECUDA, std::string("ROI kernel launch: ") + cudaGetErrorString(ce));
+      ++e->launches;
+      return FLOPE_OK;
+    }
+  }
   // ---- staged kernels: frame rows whose alignment modulo 4 does not depend on the row, output side up to 512 ----
   if (e->roi_staged && W % 4 == 0 && S <= 512 && n_frames >= 1 && (out_fmt != FLOPE_OUT_ENGINE || rp.g.plane * 16 < (1LL << 32))) {
     rp.frames_end = d_frames + (long long)(n_frames - 1) * frame_stride + (long long)H * W * 3;
@@ -1275,6 +1338,23 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
     return FLOPE_OK;
   }
   if (!std::strcmp(key, "roi_staged")) { e->roi_staged = value != 0; return FLOPE_OK; }
+  if (!std::strcmp(key, "roi_stream")) { e->roi_stream = value; return FLOPE_OK; }
+  if (!std::strcmp(key, "roi_item_rows") || !std::strcmp(key, "roi_item_rows8")) {
+    if (value < 1 || value > kR3MaxItemRows) return fail(FLOPE_EINVAL, "roi_item_rows must be in [1,64]");
+    (key[13] ? e->roi_item_rows8 : e->roi_item_rows) = value;
+    return FLOPE_OK;
+  }
+  if (!std::strcmp(key, "roi_stage_kb")) {
+    if (value < 1 || value > 64) return fail(FLOPE_EINVAL, "roi_stage_kb must be in [1,64]");
+    e->roi_stage_kb = value;
+    return FLOPE_OK;
+  }
+  if (!std::strcmp(key, "roi_stages")) {
+    if (value < 2 || value > kR3MaxStages) return fail(FLOPE_EINVAL, "roi_stages must be in [2,8]");
+    e->roi_stages = value;
+    return FLOPE_OK;
+  }
+  if (!std::strcmp(key, "roi_ctas_per_sm")) { e->roi_ctas_per_sm = value; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_lut")) { e->roi_lut = value != 0; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_sub")) {
     if (value < 1 || value > 8) return fail(FLOPE_EINVAL, "roi_sub must be in [1,8]");

@@ -1,0 +1,451 @@
+// flope_b200: streaming ROI crop / resize / mask / normalise kernels (sm_100a) - the production path.
+//
+// Same arithmetic as roi_crop.cuh (cv2's uint8 fixed-point resize, bit for bit; see the header there and
+// oracle/resize.py), organised as a persistent, warp-specialised pipeline:
+//
+//   work item   = (crop, strip of `rows_per_item` output rows), all S output columns; items are dealt round-robin
+//                 to the CTAs of a grid sized to the machine (CTAs per SM x SMs).
+//   producer    = the last warp of the CTA.  Per item it writes a header and the vertical table (per output row:
+//                 the source row that completes it, the two/eight coefficients, the output row offset) into one
+//                 of two item slots, then streams the item's source rows - image and mask - through a ring of
+//                 shared-memory stages with one TMA bulk copy per row and matrix (16-byte aligned superset of the
+//                 row segment, so every DRAM sector is fetched once).  Rows outside the crop are the clamped row:
+//                 the replicated border of cv2 costs the consumers nothing.
+//   consumers   = one thread per output column (two columns S/2 apart for S > 256).  A thread walks DOWN the
+//                 source rows as they arrive: horizontal filter of the row into registers (aligned 32-bit words,
+//                 funnel shift, byte permute, DP2A), then every output row this source row completes is emitted
+//                 (vertical filter, mask, normalise, store).  Source rows are filtered once per strip and column,
+//                 raw rows are dead as soon as they are filtered, so a stage is handed back to the producer after
+//                 a few rows: the ring is small (3 x ~10 KB), several CTAs fit an SM and loads run ahead of compute.
+//
+// Requirements checked by the host (engine.cu: run_roi): W % 16 == 0 (the 16-byte phase of a row segment is the
+// same for every row of a crop), S even and <= 512, rows fit a stage.  Anything else takes roi_crop_kernel.
+#pragma once
+#include "roi_crop.cuh"
+
+namespace flope {
+
+struct Roi3Params {
+  const uint8_t* frames;      // (n_frames, H, W, 3) u8
+  long long frame_stride;
+  const uint8_t* masks;       // (n_frames, H, W) u8 or nullptr
+  long long mask_stride;
+  int W;
+  const int32_t* boxes;       // (n, 5): frame, xmin, ymin, xmax, ymax
+  int n;
+  int S;
+  int out_fmt;
+  void* out;
+  Geom g;                     // fmt 1 geometry
+  int rows_per_item;          // output rows per work item (<= kR3MaxItemRows)
+  int items_per_crop;
+  int n_items;
+  int stage_bytes;            // multiple of 128
+  int n_stages;               // <= kR3MaxStages
+  int xtab_slot;              // S * 16
+  int ring_off;               // kR3Xtab + 2 * xtab_slot, multiple of 128
+};
+
+constexpr int kR3MaxItemRows = 64;
+constexpr int kR3MaxStages = 8;
+// shared-memory map (bytes)
+constexpr int kR3Full = 0;                     // mbarrier per stage: rows have landed
+constexpr int kR3Empty = 64;                   // mbarrier per stage: every consumer warp is done with the rows
+constexpr int kR3ItemFull = 128;               // mbarrier per item slot: header + vertical table written
+constexpr int kR3ItemEmpty = 144;              // mbarrier per item slot: every consumer warp is done with them
+constexpr int kR3Hdr = 192;                    // 2 x 64 B
+constexpr int kR3Ytab = 320;                   // 2 x (kR3MaxItemRows + 1) entries
+constexpr int kR3YtabEntry2 = 16;              // linear : {u_top, float b0 * 2^-20, float b1 * 2^-20, output row offset}
+constexpr int kR3YtabEntry8 = 48;              // lanczos: {u_top, output row offset, 0, 0, int coef[8] by ring slot}
+constexpr int kR3YtabSlot = (kR3MaxItemRows + 1) * kR3YtabEntry8;
+constexpr int kR3Lut = 7168;                   // 256 x u32, 1 KB aligned
+constexpr int kR3Xtab = 8192;                  // 2 x S columns x 16 B: per-column constants of the item (horizontal table);
+                                               // the ring follows at Roi3Params::ring_off
+constexpr int kR3RingTail = 64;                // over-read of the last row's window
+static_assert(kR3Ytab + 2 * kR3YtabSlot <= kR3Lut, "item slots overlap the table");
+
+// header words
+enum { R3H_VALID = 0, R3H_CROP, R3H_UFIRST, R3H_NROWS, R3H_K, R3H_PITCH, R3H_MOFF, R3H_MISI, R3H_MISM, R3H_SW };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t r3_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t r3_lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ U32x4 r3_lds128(uint32_t a) {
+  U32x4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void r3_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void r3_sts128(uint32_t a, U32x4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void r3_bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void r3_bar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void r3_bar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a pipeline bug must trap (a visible CUDA error), never hang the box.  try_wait suspends the
+// thread for a hardware-defined interval, so the loop is not a hot spin.
+__device__ __forceinline__ void r3_bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+    if (ok) return;
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void r3_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct R3Col2 {             // bilinear
+  uint32_t iofs;            // byte offset (from the row slot) of the aligned word that holds the first tap byte
+  uint32_t ish;             // 8 * misalignment of the first tap byte
+  uint32_t cx;              // a0 | a1 << 16
+  uint32_t mofs;            // same for the mask row
+  uint32_t msel;            // byte-permute selector of the two mask taps
+};
+__device__ __forceinline__ R3Col2 r3_col2(int x, double scale_x, int sw, uint32_t mis_i, uint32_t moff, uint32_t mis_m) {
+  short ic[2];
+  int sx;
+  linear_coefs(x, scale_x, sw, false, sx, ic);
+  R3Col2 k;
+  k.cx = (uint32_t)(uint16_t)ic[0] | ((uint32_t)(uint16_t)ic[1] << 16);
+  const uint32_t bo = mis_i + 3u * (uint32_t)sx;
+  k.iofs = bo & ~3u;
+  k.ish = 8u * (bo & 3u);
+  const uint32_t bm = moff + mis_m + (uint32_t)sx;
+  k.mofs = bm & ~3u;
+  k.msel = (bm & 3u) | (((bm & 3u) + 1u) << 4);
+  return k;
+}
+// ---------------------------------------------------------------------------------------------
+// producer warp
+// ---------------------------------------------------------------------------------------------
+template <int TAPS, bool HAS_MASK>
+__device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, int lane) {
+  constexpr int LO = TAPS == 8 ? 3 : 0;          // first / last tap relative to floor(source coordinate)
+  constexpr int HI = TAPS == 8 ? 4 : 1;
+  constexpr int YE = TAPS == 8 ? kR3YtabEntry8 : kR3YtabEntry2;
+  uint32_t stage = 0, sphase = 0;
+  int it = 0;
+  for (int item = blockIdx.x;; item += gridDim.x) {
+    const int b = it & 1;
+    r3_bar_wait(sb + kR3ItemEmpty + 8 * b, (((uint32_t)it >> 1) & 1u) ^ 1u);
+    const uint32_t hdr = sb + kR3Hdr + 64 * b;
+    if (item >= p.n_items) {
+      if (lane == 0) { r3_sts32(hdr + 4 * R3H_VALID, 0u); r3_bar_arrive(sb + kR3ItemFull + 8 * b); }
+      return;
+    }
+    const int crop = item / p.items_per_crop, strip = item - crop * p.items_per_crop;
+    const int32_t* bx = p.boxes + (size_t)crop * 5;
+    const int frame = __ldg(bx), xmin = __ldg(bx + 1), ymin = __ldg(bx + 2);
+    const int sw = __ldg(bx + 3) - xmin, sh = __ldg(bx + 4) - ymin;
+    if (sw <= 0 || sh <= 0) continue;            // empty box: nothing to write (the host rejects these)
+    const int S = p.S;
+    const int y_begin = strip * p.rows_per_item, y_end = imin(S, y_begin + p.rows_per_item);
+    const int n_out = y_end - y_begin;
+    const double scale_y = axis_scale(sh, S);
+    float f;
+    const int u_first = src_coord(y_begin, scale_y, f) - LO;
+    const int u_last = src_coord(y_end - 1, scale_y, f) + HI;
+    int n_rows = u_last - u_first + 1;
+    if (TAPS == 2) n_rows = (n_rows + 1) & ~1;   // the bilinear consumers take rows in pairs
+    // ---- vertical table ----
+    const uint32_t ytab = sb + kR3Ytab + kR3YtabSlot * b;
+    for (int i = lane; i <= n_out; i += 32) {
+      const int y = y_begin + i;
+      uint32_t ooff;
+      if (p.out_fmt == 0) ooff = (uint32_t)y * (uint32_t)S * 4u;
+      else ooff = (uint32_t)(y >> 1) * (uint32_t)p.g.Wp * 16u + ((y & 1) ? (uint32_t)(p.g.plane * 16) : 0u);
+      if (TAPS == 2) {
+        U32x4 e;
+        if (i == n_out) { e.x = 0x7FFFFFFFu; e.y = e.z = e.w = 0u; }
+        else {
+          short ic[2]; int sy;
+          linear_coefs(y, scale_y, sh, true, sy, ic);
+          e.x = (uint32_t)(sy + 1); e.w = ooff;
+          e.y = __float_as_uint((float)ic[0] * 9.5367431640625e-07f);      // b * 2^-20, exact
+          e.z = __float_as_uint((float)ic[1] * 9.5367431640625e-07f);
+        }
+        r3_sts128(ytab + i * YE, e);
+      } else {
+        U32x4 e0, e1, e2;
+        e0.y = ooff; e0.z = e0.w = 0u;
+        if (i == n_out) { e0.x = 0x7FFFFFFFu; e1.x = e1.y = e1.z = e1.w = e2.x = e2.y = e2.z = e2.w = 0u; }
+        else {
+          short ic[8]; int sy;
+          lanczos4_coefs(y, scale_y, sy, ic);
+          e0.x = (uint32_t)(sy + 4);
+          int cf[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cf[j] = 0;
+          // ring slot k holds the source row u with (u & 7) == k; the window is u = sy - 3 + j
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int slot = (sy - 3 + j) & 7;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k == slot) cf[k] = (int)ic[j];
+          }
+          e1.x = cf[0]; e1.y = cf[1]; e1.z = cf[2]; e1.w = cf[3];
+          e2.x = cf[4]; e2.y = cf[5]; e2.z = cf[6]; e2.w = cf[7];
+        }
+        r3_sts128(ytab + i * YE, e0); r3_sts128(ytab + i * YE + 16, e1); r3_sts128(ytab + i * YE + 32, e2);
+      }
+    }
+    // ---- header ----
+    const uint8_t* img0 = p.frames + (long long)frame * p.frame_stride + ((long long)ymin * p.W + xmin) * 3;
+    const uint8_t* msk0 = HAS_MASK ? p.masks + (long long)frame * p.mask_stride + (long long)ymin * p.W + xmin : nullptr;
+    const uint32_t mis_i = (uint32_t)((uintptr_t)img0 & 15), mis_m = (uint32_t)((uintptr_t)msk0 & 15);
+    const uint32_t Li = (mis_i + 3u * (uint32_t)sw + 15u) & ~15u;
+    const uint32_t Lm = HAS_MASK ? (mis_m + (uint32_t)sw + 15u) & ~15u : 0u;
+    const uint32_t pitch = Li + Lm;
+    int K = imin(32, p.stage_bytes / (int)pitch);
+    if (TAPS == 2) K &= ~1;
+    if (TAPS == 2) {
+      const double scale_x = axis_scale(sw, S);
+      for (int x = lane; x < S; x += 32) {
+        const R3Col2 k = r3_col2(x, scale_x, sw, mis_i, Li, mis_m);
+        U32x4 e;
+        e.x = k.iofs | (k.ish << 16); e.y = k.cx; e.z = k.mofs | (k.msel << 16); e.w = 0u;
+        r3_sts128(sb + kR3Xtab + p.xtab_slot * b + 16 * x, e);
+      }
+    }
+    if (lane == 0) {
+      r3_sts32(hdr + 4 * R3H_CROP, (uint32_t)crop); r3_sts32(hdr + 4 * R3H_UFIRST, (uint32_t)u_first);
+      r3_sts32(hdr + 4 * R3H_NROWS, (uint32_t)n_rows); r3_sts32(hdr + 4 * R3H_K, (uint32_t)K);
+      r3_sts32(hdr + 4 * R3H_PITCH, pitch); r3_sts32(hdr + 4 * R3H_MOFF, Li);
+      r3_sts32(hdr + 4 * R3H_MISI, mis_i); r3_sts32(hdr + 4 * R3H_MISM, mis_m);
+      r3_sts32(hdr + 4 * R3H_SW, (uint32_t)sw); r3_sts32(hdr + 4 * R3H_VALID, 1u);
+    }
+    __syncwarp();
+    if (lane == 0) r3_bar_arrive(sb + kR3ItemFull + 8 * b);
+    // ---- rows ----
+    const long long rb_i = (long long)p.W * 3, rb_m = p.W;
+    for (int r0 = 0; r0 < n_rows; r0 += K) {
+      const int k_this = imin(K, n_rows - r0);
+      r3_bar_wait(sb + kR3Empty + 8 * stage, sphase ^ 1u);
+      const uint32_t full = sb + kR3Full + 8 * stage;
+      if (lane == 0) r3_bar_expect(full, (uint32_t)k_this * pitch);
+      __syncwarp();
+      if (lane < k_this) {
+        const int r = iclamp(u_first + r0 + lane, 0, sh - 1);
+        const uint32_t dst = sb + (uint32_t)p.ring_off + stage * (uint32_t)p.stage_bytes + (uint32_t)lane * pitch;
+        r3_bulk_g2s(dst, img0 - mis_i + r * rb_i, Li, full);
+        if (HAS_MASK) r3_bulk_g2s(dst + Li, msk0 - mis_m + r * rb_m, Lm, full);
+      }
+      if (++stage == (uint32_t)p.n_stages) { stage = 0; sphase ^= 1u; }
+    }
+    ++it;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// consumers: per-column constants and the horizontal filters
+// ---------------------------------------------------------------------------------------------
+// Horizontally filtered source row for cv2's vertical pass, which consumes A = S >> 4 (S = a0 * p0 + a1 * p1 < 2^20).
+// The vertical pass runs on the FMA pipe (see r3_emit2), so the value is kept as the float 2^23 + 16 * A: its bit
+// pattern is 0x4B000000 | (S & ~15), one logic operation on the DP2A result.
+__device__ __forceinline__ uint32_t r3_f16a(uint32_t S) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, 0xFFFFF0, %2, 0xEA;" : "=r"(d) : "r"(S), "r"(0x4B000000u));
+  return d;
+}
+template <bool HAS_MASK>
+__device__ __forceinline__ void r3_hfilt2(uint32_t row, const R3Col2& k, uint32_t (&dst)[HAS_MASK ? 4 : 3]) {
+  const uint32_t wa = row + k.iofs;
+  const uint32_t w0 = r3_lds32(wa), w1 = r3_lds32(wa + 4), w2 = r3_lds32(wa + 8);
+  const uint32_t u0 = __funnelshift_r(w0, w1, k.ish), u1 = __funnelshift_r(w1, w2, k.ish);   // a0 a1 a2 b0 | b1 b2 . .
+  const uint32_t r1 = __byte_perm(u0, u1, 0x4130);                                           // a0 b0 a1 b1
+  const uint32_t r2 = __byte_perm(u0, u1, 0x0052);                                           // a2 b2 . .
+  dst[0] = r3_f16a(__dp2a_lo(k.cx, r1, 0u));
+  dst[1] = r3_f16a(__dp2a_hi(k.cx, r1, 0u));
+  dst[2] = r3_f16a(__dp2a_lo(k.cx, r2, 0u));
+  if (HAS_MASK) {
+    const uint32_t ma = row + k.mofs;
+    const uint32_t r3 = __byte_perm(r3_lds32(ma), r3_lds32(ma + 4), k.msel);
+    dst[HAS_MASK ? 3 : 0] = r3_f16a(__dp2a_lo(k.cx, r3, 0u));
+  }
+}
+
+// One output pixel.  cv2's vertical pass is ((b0 * A0 >> 16) + (b1 * A1 >> 16) + 2) >> 2 with two separate truncations.
+// Both happen on the FMA pipe: with F = 2^23 + 16 A (r3_hfilt2), bf = b * 2^-20 and round-toward-minus-infinity,
+//   fma.rm(bf0, F0, M0)          = M0 + 8 b0 + floor(b0 A0 / 65536)              (exact: one rounding, ulp 1 in [2^23, 2^24))
+//   fma.rm(bf1, F1, the above)   = M0 + 8 (b0 + b1) + floor(..) + floor(..)
+// so M0 = 1.5 * 2^23 + 2 - 8 (b0 + b1) leaves the bit pattern 0x4B400000 + v4, v4 = 4 x the cv2 result + (0..3).
+//   fmt 1: two 32-bit words [c0 c1 | c2 0] of bf16;  bf16_rn(fl(4v * fl(1/1020))) == bf16_rn(fp32(v / 255)) for all v
+//   fmt 0: three fp32 words; unmasked values come from the 256-entry table in shared memory
+// The branches are warp-uniform (votes): a warp whose 32 pixels are all masked out skips the image channels, a warp
+// with a partially masked pixel (mask edge) takes the general quotient for every lane, everything else takes the
+// unmasked path and zeroes its masked-out lanes with a select.
+__device__ __forceinline__ float r3_fma_rm(float a, float b, float c) {
+  float d;
+  asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+template <bool HAS_MASK, int FMT>
+__device__ __forceinline__ void r3_emit2(const uint32_t (&lo)[HAS_MASK ? 4 : 3], const uint32_t (&up)[HAS_MASK ? 4 : 3],
+                                         const U32x4& yt, uint8_t* out, uint32_t plane_bytes, uint32_t lut) {
+  constexpr int NCH = HAS_MASK ? 4 : 3;
+  constexpr uint32_t kBase = 0x4B400000u;    // 1.5 * 2^23
+  const float b0 = __uint_as_float(yt.y), b1 = __uint_as_float(yt.z);
+  const float m0 = fmaf(b0 + b1, -8388608.0f, 12582914.0f);
+  uint32_t o[3];
+  uint32_t m4 = kBase + 1020u;
+  if (HAS_MASK) m4 = __float_as_uint(r3_fma_rm(b1, __uint_as_float(up[NCH - 1]), r3_fma_rm(b0, __uint_as_float(lo[NCH - 1]), m0)));
+  const bool off = HAS_MASK && m4 < kBase + 4u;      // masked out: exactly zero whatever the image holds
+  if (HAS_MASK && !__any_sync(0xFFFFFFFFu, !off)) {
+    o[0] = o[1] = o[2] = 0u;
+  } else {
+    uint32_t v4[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v4[j] = __float_as_uint(r3_fma_rm(b1, __uint_as_float(up[j]), r3_fma_rm(b0, __uint_as_float(lo[j]), m0)));
+    if (HAS_MASK && __any_sync(0xFFFFFFFFu, m4 - (kBase + 4u) < 1016u)) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[c] = __float_as_uint(normalise_u8((int)((v4[c] >> 2) & 0xFFu), (int)((m4 >> 2) & 0xFFu)));
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (FMT == 0) {
+          o[c] = r3_lds32((v4[c] & 0x3FCu) | lut);
+        } else {
+          // (float)(4v) without a conversion: the integer sits in the mantissa of 2^23 + 4v
+          uint32_t xb;
+          asm("lop3.b32 %0, %1, 0x3FC, %2, 0xEA;" : "=r"(xb) : "r"(v4[c]), "r"(0x4B000000u));
+          o[c] = __float_as_uint(fmaf(__uint_as_float(xb), 1.0f / 1020.0f, -8388608.0f * (1.0f / 1020.0f)));
+        }
+        if (FMT == 0 && HAS_MASK) o[c] = off ? 0u : o[c];
+      }
+    }
+  }
+  if (FMT == 0) {
+    uint8_t* q = out + yt.w;
+    *reinterpret_cast<uint32_t*>(q) = o[0];
+    *reinterpret_cast<uint32_t*>(q + plane_bytes) = o[1];
+    *reinterpret_cast<uint32_t*>(q + 2 * (size_t)plane_bytes) = o[2];
+  } else {
+    uint2 v;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(v.x) : "f"(__uint_as_float(o[1])), "f"(__uint_as_float(o[0])));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(v.y) : "f"(0.f), "f"(__uint_as_float(o[2])));
+    if (HAS_MASK) { v.x = off ? 0u : v.x; v.y = off ? 0u : v.y; }
+    *reinterpret_cast<uint2*>(out + yt.w) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear consumer
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_MASK, int FMT, int NCOL>
+__device__ __forceinline__ void r3_consumer2(const Roi3Params& p, uint32_t sb, int t, int lane) {
+  constexpr int NCH = HAS_MASK ? 4 : 3;
+  const int S = p.S;
+  const uint32_t lut = sb + kR3Lut;
+  const uint32_t ring_end = sb + (uint32_t)p.ring_off + (uint32_t)p.n_stages * (uint32_t)p.stage_bytes;
+  const uint32_t bars_end = sb + kR3Full + 8u * (uint32_t)p.n_stages;
+  uint32_t stage_row = sb + (uint32_t)p.ring_off, full = sb + kR3Full, sphase = 0;    // ring position; `empty` sits kR3Empty behind `full`
+  uint8_t* out0[NCOL];
+  uint32_t plane_bytes = 0u;
+#pragma unroll
+  for (int c = 0; c < NCOL; ++c) {
+    const int x = t + c * (S / NCOL);
+    if (FMT == 0) {
+      out0[c] = reinterpret_cast<uint8_t*>(p.out) + (long long)x * 4;
+      plane_bytes = (uint32_t)S * (uint32_t)S * 4u;
+    } else {
+      out0[c] = reinterpret_cast<uint8_t*>(p.out) + (long long)p.g.base * 16 + (long long)(x >> 1) * 16 + (x & 1) * 8;
+    }
+  }
+  const long long crop_bytes = FMT == 0 ? 3LL * S * S * 4 : (long long)p.g.Hp * p.g.Wp * 16;
+  for (int it = 0;; ++it) {
+    const int b = it & 1;
+    r3_bar_wait(sb + kR3ItemFull + 8 * b, ((uint32_t)it >> 1) & 1u);
+    const uint32_t hdr = sb + kR3Hdr + 64 * b;
+    const U32x4 h0 = r3_lds128(hdr), h1 = r3_lds128(hdr + 16);
+    if (h0.x == 0u) return;
+    const int crop = (int)h0.y;
+    int u = (int)h0.z, rows_left = (int)h0.w;
+    const int K = (int)h1.x;
+    const uint32_t pitch = h1.y;
+    R3Col2 col[NCOL];
+    uint8_t* out[NCOL];
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) {
+      const U32x4 e = r3_lds128(sb + kR3Xtab + p.xtab_slot * b + 16 * (t + c * (S / NCOL)));
+      col[c].iofs = e.x & 0xFFFFu; col[c].ish = e.x >> 16; col[c].cx = e.y; col[c].mofs = e.z & 0xFFFFu; col[c].msel = e.z >> 16;
+      out[c] = out0[c] + crop * crop_bytes;
+    }
+    uint32_t A[NCOL][NCH], B[NCOL][NCH];
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c)
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) A[c][j] = B[c][j] = 0u;
+    uint32_t ya = sb + kR3Ytab + kR3YtabSlot * b;
+    U32x4 yt = r3_lds128(ya);
+    while (rows_left > 0) {
+      const int k_this = imin(K, rows_left);
+      rows_left -= k_this;
+      r3_bar_wait(full, sphase);
+      uint32_t row = stage_row;
+      for (int k = 0; k < k_this; k += 2) {
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) r3_hfilt2<HAS_MASK>(row, col[c], A[c]);
+        while ((int)yt.x == u) {             // output rows whose upper source row is u
+#pragma unroll
+          for (int c = 0; c < NCOL; ++c) r3_emit2<HAS_MASK, FMT>(B[c], A[c], yt, out[c], plane_bytes, lut);
+          ya += kR3YtabEntry2;
+          yt = r3_lds128(ya);
+        }
+        ++u; row += pitch;
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) r3_hfilt2<HAS_MASK>(row, col[c], B[c]);
+        while ((int)yt.x == u) {
+#pragma unroll
+          for (int c = 0; c < NCOL; ++c) r3_emit2<HAS_MASK, FMT>(A[c], B[c], yt, out[c], plane_bytes, lut);
+          ya += kR3YtabEntry2;
+          yt = r3_lds128(ya);
+        }
+        ++u; row += pitch;
+      }
+      __syncwarp();
+      if (lane == 0) r3_bar_arrive(full + kR3Empty);
+      stage_row += (uint32_t)p.stage_bytes; full += 8u;
+      if (full == bars_end) { stage_row = sb + (uint32_t)p.ring_off; full = sb + kR3Full; sphase ^= 1u; }
+    }
+    __syncwarp();
+    if (lane == 0) r3_bar_arrive(sb + kR3ItemEmpty + 8 * b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel: blockDim = 32 * (consumer warps + 1); consumer thread t owns output columns t + c * S / NCOL
+// ---------------------------------------------------------------------------------------------
+template <int TAPS, bool HAS_MASK, int FMT, int NCOL>
+__global__ void __launch_bounds__(NCOL == 1 ? 256 : 288) roi3_kernel(const __grid_constant__ Roi3Params p) {
+  extern __shared__ __align__(1024) uint8_t r3_smem[];
+  const uint32_t sb = smem_u32(r3_smem);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n_cons = (int)(blockDim.x >> 5) - 1;
+  if (t == 0) {
+    if (sb & 1023u) __trap();
+    for (int s = 0; s < p.n_stages; ++s) { r3_bar_init(sb + kR3Full + 8 * s, 1u); r3_bar_init(sb + kR3Empty + 8 * s, (uint32_t)n_cons); }
+    for (int b = 0; b < 2; ++b) { r3_bar_init(sb + kR3ItemFull + 8 * b, 1u); r3_bar_init(sb + kR3ItemEmpty + 8 * b, (uint32_t)n_cons); }
+    mbar_fence_init();
+  }
+  if (FMT == 0) for (int i = t; i < 256; i += blockDim.x) r3_sts32(sb + kR3Lut + 4 * i, f32_bits(normalise_u8(i, 255)));
+  __syncthreads();
+  if (warp == n_cons) {
+    r3_producer<TAPS, HAS_MASK>(p, sb, lane);
+  } else if (t < p.S / NCOL) {
+    r3_consumer2<HAS_MASK, FMT, NCOL>(p, sb, t, lane);
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace flope

@@ -43,6 +43,17 @@ def report(tag, ms, byts, nn):
 eng = _lib.Engine(0, max_batch=n, crop_hw=224)
 by_m = float((4 * side ** 2 + 301056 + 20).sum())
 by_n = float((3 * side ** 2 + 301056 + 20).sum())
+scfgs = [(28, 10, 3, 0)] if quick else [(28, 10, 3, 0), (32, 10, 3, 0), (56, 10, 3, 0), (16, 10, 3, 0), (28, 6, 4, 0), (28, 16, 3, 0),
+                                        (28, 10, 2, 0), (28, 10, 3, 4), (28, 10, 3, 3), (112, 10, 3, 0)]
+for rows, kb, stages, per_sm in scfgs:
+    eng.debug_set("roi_item_rows", rows); eng.debug_set("roi_stage_kb", kb); eng.debug_set("roi_stages", stages)
+    eng.debug_set("roi_ctas_per_sm", per_sm)
+    for mask_on in (True, False):
+        m = mk if mask_on else None
+        ms = timeit(lambda: eng.roi_crop(fr, m, bx, 224, _lib.INTERP_LINEAR, out_fmt=_lib.OUT_ENGINE))
+        report(f"stream rows={rows} kb={kb} stages={stages} per_sm={per_sm} bilinear->224 bf16 engine mask={int(mask_on)}", ms,
+               by_m if mask_on else by_n, n)
+eng.debug_set("roi_stream", 0)
 eng.debug_set("roi_staged", 0)
 ms = timeit(lambda: eng.roi_crop(fr, mk, bx, 224, _lib.INTERP_LINEAR, out_fmt=_lib.OUT_ENGINE))
 report("generic  bilinear->224 bf16 engine mask=1", ms, by_m, n)
@@ -63,6 +74,9 @@ eng = _lib.Engine(0, max_batch=8, crop_hw=512)
 out = torch.empty((nb, 3, 512, 512), device="cuda")
 s = side[:nb]
 byts = float((4 * s ** 2 + 3145728 + 20).sum())
+ms = timeit(lambda: eng.roi_crop(fr, mk, bx[:nb], 512, _lib.INTERP_LINEAR, out=out), reps=5)
+report("stream bilinear->512 f32 NCHW mask=1", ms, byts, nb)
+eng.debug_set("roi_stream", 0)
 eng.debug_set("roi_staged", 0)
 for interp, name in ((_lib.INTERP_LANCZOS4, "lanczos4"), (_lib.INTERP_LINEAR, "bilinear")):
     ms = timeit(lambda: eng.roi_crop(fr, mk, bx[:nb], 512, interp, out=out), reps=5)
