@@ -177,7 +177,7 @@ struct flope_engine {
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
   int roi_stream = 1;                            // streaming ROI kernels (roi3_kernel, roi_stream.cuh): the production path
   int roi_item_rows = 28;                        // output rows per work item of the streaming bilinear kernel
-  int roi_item_rows8 = 32;                       // same for the streaming Lanczos4 kernel
+  int roi_item_rows8 = 128;                       // same for the streaming Lanczos4 kernel
   int roi_stage_kb = 10;                         // bytes per ring stage of the streaming kernels
   int roi_stages = 3;                            // ring depth
   int roi_ctas_per_sm = 0;                       // 0 = as many as fit
@@ -195,6 +195,8 @@ struct flope_engine {
   int chain_dynamic = 0;                     // chains claim work items from an atomic counter (safe under partial residency)
   bool use_chain = true;                         // one persistent launch per ResNet stage (four convs) with per-tile completion flags
   std::vector<std::vector<int>> chains;          // layer indices of each stage
+  unsigned int* d_roi_sched = nullptr;           // work counter of the streaming ROI kernels (self-resetting)
+  int roi_dynamic = 1;                           // streaming ROI kernels claim items from the counter (0 = static round-robin)
   uint32_t* d_flags = nullptr;                   // completion counters of all chains, zeroed at the start of every forward
   size_t flags_per_chain = 0;                    // counters reserved per chain (kMaxChain layers x position tiles at max_batch)
   bool small_tiles = true;                       // latency-oriented tiles when max_batch is too small to fill the SMs
@@ -808,25 +810,26 @@ cudaError_t roi2_launch(const RoiParams& rp, dim3 grid, int block, size_t smem, 
 }
 
 // streaming ROI kernels (roi_stream.cuh): persistent grid, CTAs per SM from the occupancy calculator
-template <int TAPS, bool HAS_MASK, int FMT, int NCOL>
+template <int TAPS, bool HAS_MASK, int FMT, int MAXT, int MINB>
 cudaError_t roi3_launch(const Roi3Params& rp, int num_sms, int ctas_per_sm, int block, size_t smem, cudaStream_t st) {
   static int occ[64] = {};                        // per device: opt in to > 48 KB of dynamic shared memory once
   static size_t occ_smem[64] = {};
+  static int occ_block[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  if (!occ[dev] || occ_smem[dev] != smem) {
-    cudaError_t ce = cudaFuncSetAttribute(roi3_kernel<TAPS, HAS_MASK, FMT, NCOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  if (!occ[dev] || occ_smem[dev] != smem || occ_block[dev] != block) {
+    cudaError_t ce = cudaFuncSetAttribute(roi3_kernel<TAPS, HAS_MASK, FMT, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (ce != cudaSuccess) return ce;
     int n = 0;
-    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, roi3_kernel<TAPS, HAS_MASK, FMT, NCOL>, block, smem);
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, roi3_kernel<TAPS, HAS_MASK, FMT, MAXT, MINB>, block, smem);
     if (ce != cudaSuccess) return ce;
     if (n < 1) return cudaErrorLaunchOutOfResources;
-    occ[dev] = n; occ_smem[dev] = smem;
+    occ[dev] = n; occ_smem[dev] = smem; occ_block[dev] = block;
   }
   const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, occ[dev]) : occ[dev];
   const int grid = std::max(1, std::min(rp.n_items, num_sms * per_sm));
-  roi3_kernel<TAPS, HAS_MASK, FMT, NCOL><<<grid, block, smem, st>>>(rp);
+  roi3_kernel<TAPS, HAS_MASK, FMT, MAXT, MINB><<<grid, block, smem, st>>>(rp);
   return cudaGetLastError();
 }
 
@@ -845,32 +848,38 @@ int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W
   const bool has_mask = d_masks != nullptr;
   const bool lanczos = interp == FLOPE_INTERP_LANCZOS4;
   ProfScope ps(e, lanczos ? "roi_crop:lanczos4" : "roi_crop:linear", st);
-  // ---- streaming kernels: 16-byte phase of a row segment independent of the row, one or two columns per thread ----
-  if (e->roi_stream && !lanczos && W % 16 == 0 && S <= 512 && S % (S <= 224 ? 32 : 64) == 0 && n_frames >= 1 && n >= 1 &&
-      (out_fmt != FLOPE_OUT_ENGINE || rp.g.plane * 16 < (1LL << 31))) {
+  // ---- streaming kernels: 16-byte phase of a row segment independent of the row, one output column per thread ----
+  const int cw = (S <= 256 && S % 32 == 0) ? S : (S <= 512 && S % 64 == 0) ? S / 2 : 0;
+  if (e->roi_stream && cw && W % 16 == 0 && n_frames >= 1 && n >= 1 && (out_fmt != FLOPE_OUT_ENGINE || rp.g.plane * 16 < (1LL << 31))) {
     Roi3Params q{};
     q.frames = d_frames; q.frame_stride = frame_stride; q.masks = d_masks; q.mask_stride = (long long)H * W; q.W = W;
     q.boxes = d_boxes; q.n = n; q.S = S; q.out_fmt = out_fmt; q.out = rp.out; q.g = rp.g;
     q.rows_per_item = std::max(1, std::min(std::min(kR3MaxItemRows, S), lanczos ? e->roi_item_rows8 : e->roi_item_rows));
-    q.items_per_crop = (S + q.rows_per_item - 1) / q.rows_per_item;
-    q.n_items = n * q.items_per_crop;
+    q.cols_per_item = cw;
+    q.col_blocks = S / cw;
+    q.items_per_crop = (S + q.rows_per_item - 1) / q.rows_per_item * q.col_blocks;
+    const long long n_items = (long long)n * q.items_per_crop;
+    q.n_items = (int)n_items;
     const int side = std::min(H, W);                 // a square in-frame box is at most this wide
-    const int max_pitch = ((15 + 3 * side + 15) & ~15) + ((15 + side + 15) & ~15);
-    q.stage_bytes = (std::max(e->roi_stage_kb * 1024, 2 * max_pitch) + 127) & ~127;
+    const int max_pitch = ((15 + 3 * side + 15) & ~15) + ((15 + side + 15) & ~15) + (lanczos ? 2 * kR3PadM + kR3PadL + kR3PadR : 0);
+    q.stage_bytes = (std::max(e->roi_stage_kb * 1024, (lanczos ? 1 : 2) * max_pitch) + 127) & ~127;
     q.n_stages = std::max(2, std::min(kR3MaxStages, e->roi_stages));
-    q.xtab_slot = S * 16;
-    q.ring_off = (kR3Xtab + 2 * q.xtab_slot + 127) & ~127;
+    q.sched = e->roi_dynamic ? e->d_roi_sched : nullptr;
+    q.xtab_slot = cw * (lanczos ? kR3XtabEntry8 : kR3XtabEntry2);
+    q.ring_off = (r3_xtab_off(lanczos ? 8 : 2) + 2 * q.xtab_slot + 127) & ~127;
     const size_t smem = (size_t)q.ring_off + (size_t)q.n_stages * q.stage_bytes + kR3RingTail;
-    if (smem <= (size_t)kMaxSmem) {
-      const int ncol = S <= 224 ? 1 : 2;
-      const int block = 32 * (S / ncol / 32 + 1);
-      const int key = (ncol == 2 ? 4 : 0) | (has_mask ? 2 : 0) | (out_fmt == FLOPE_OUT_ENGINE ? 1 : 0);
+    if (smem <= (size_t)kMaxSmem && n_items < (1LL << 30)) {
+      const int block = cw + 32;
+      const int key = (lanczos ? 4 : 0) | (has_mask ? 2 : 0) | (out_fmt == FLOPE_OUT_ENGINE ? 1 : 0);
       cudaError_t ce;
-#define ROI3_CASE(K, M, F, C) case K: ce = roi3_launch<2, M, F, C>(q, e->num_sms, e->roi_ctas_per_sm, block, smem, st); break;
+      // up to 224 columns per item: 256 threads, five CTAs per SM (<= 48 registers); wider items: 288 threads
+#define ROI3_CASE(K, T, M, F) case K: ce = block <= 256 ? roi3_launch<T, M, F, 256, (T == 2 ? 5 : 3)>(q, e->num_sms, e->roi_ctas_per_sm, block, smem, st) \
+                                                       : roi3_launch<T, M, F, 288, (T == 2 ? 4 : 2)>(q, e->num_sms, e->roi_ctas_per_sm, block, smem, st); break;
       switch (key) {
-        ROI3_CASE(0, false, 0, 1) ROI3_CASE(1, false, 1, 1) ROI3_CASE(2, true, 0, 1) ROI3_CASE(3, true, 1, 1)
-        ROI3_CASE(4, false, 0, 2) ROI3_CASE(5, false, 1, 2) ROI3_CASE(6, true, 0, 2)
-        default: ce = roi3_launch<2, true, 1, 2>(q, e->num_sms, e->roi_ctas_per_sm, block, smem, st); break;
+        ROI3_CASE(0, 2, false, 0) ROI3_CASE(1, 2, false, 1) ROI3_CASE(2, 2, true, 0) ROI3_CASE(3, 2, true, 1)
+        ROI3_CASE(4, 8, false, 0) ROI3_CASE(5, 8, false, 1) ROI3_CASE(6, 8, true, 0)
+        ROI3_CASE(7, 8, true, 1)
+        default: ce = cudaErrorInvalidValue; break;
       }
 #undef ROI3_CASE
       if (ce != cudaSuccess) return fail(FLOPE_ECUDA, std::string("ROI kernel launch: ") + cudaGetErrorString(ce));
@@ -975,6 +984,8 @@ int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_
   CUDA_TRY(cudaMalloc(&e->d_feat, (size_t)(e->max_batch + kMaxTM) * e->feat_dim * sizeof(float)));
   CUDA_TRY(cudaMalloc(&e->d_wrot, (size_t)9 * e->feat_dim * sizeof(float)));
   CUDA_TRY(cudaMalloc(&e->d_brot, 9 * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&e->d_roi_sched, 2 * sizeof(unsigned int)));
+  CUDA_TRY(cudaMemset(e->d_roi_sched, 0, 2 * sizeof(unsigned int)));
   CUDA_TRY(cudaMalloc(&e->d_r9, (size_t)e->max_batch * 9 * sizeof(float)));
   for (ConvLayer& L : e->layers)
     if ((rc = plan_conv(e, L))) { flope_engine_destroy(e); return rc; }
@@ -1003,6 +1014,7 @@ void flope_engine_destroy(flope_engine* e) {
   for (ConvLayer& L : e->layers) { cudaFree(L.d_w); cudaFree(L.d_bias); }
   cudaFree(e->stem_pool.d_w); cudaFree(e->stem_pool.d_bias);
   cudaFree(e->d_flags);
+  cudaFree(e->d_roi_sched);
   cudaFree(e->d_stamps);
   cudaFree(e->d_feat); cudaFree(e->d_wrot); cudaFree(e->d_brot); cudaFree(e->d_r9);
   delete e;
@@ -1340,7 +1352,7 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
   if (!std::strcmp(key, "roi_staged")) { e->roi_staged = value != 0; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_stream")) { e->roi_stream = value; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_item_rows") || !std::strcmp(key, "roi_item_rows8")) {
-    if (value < 1 || value > kR3MaxItemRows) return fail(FLOPE_EINVAL, "roi_item_rows must be in [1,64]");
+    if (value < 1 || value > kR3MaxItemRows) return fail(FLOPE_EINVAL, "roi_item_rows must be in [1,128]");
     (key[13] ? e->roi_item_rows8 : e->roi_item_rows) = value;
     return FLOPE_OK;
   }
@@ -1354,6 +1366,7 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
     e->roi_stages = value;
     return FLOPE_OK;
   }
+  if (!std::strcmp(key, "roi_dynamic")) { e->roi_dynamic = value; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_ctas_per_sm")) { e->roi_ctas_per_sm = value; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_lut")) { e->roi_lut = value != 0; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_sub")) {

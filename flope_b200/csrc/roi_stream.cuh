@@ -3,23 +3,32 @@
 // Same arithmetic as roi_crop.cuh (cv2's uint8 fixed-point resize, bit for bit; see the header there and
 // oracle/resize.py), organised as a persistent, warp-specialised pipeline:
 //
-//   work item   = (crop, strip of `rows_per_item` output rows), all S output columns; items are dealt round-robin
-//                 to the CTAs of a grid sized to the machine (CTAs per SM x SMs).
-//   producer    = the last warp of the CTA.  Per item it writes a header and the vertical table (per output row:
-//                 the source row that completes it, the two/eight coefficients, the output row offset) into one
-//                 of two item slots, then streams the item's source rows - image and mask - through a ring of
-//                 shared-memory stages with one TMA bulk copy per row and matrix (16-byte aligned superset of the
-//                 row segment, so every DRAM sector is fetched once).  Rows outside the crop are the clamped row:
-//                 the replicated border of cv2 costs the consumers nothing.
-//   consumers   = one thread per output column (two columns S/2 apart for S > 256).  A thread walks DOWN the
-//                 source rows as they arrive: horizontal filter of the row into registers (aligned 32-bit words,
-//                 funnel shift, byte permute, DP2A), then every output row this source row completes is emitted
-//                 (vertical filter, mask, normalise, store).  Source rows are filtered once per strip and column,
-//                 raw rows are dead as soon as they are filtered, so a stage is handed back to the producer after
-//                 a few rows: the ring is small (3 x ~10 KB), several CTAs fit an SM and loads run ahead of compute.
+//   work item   = (crop, strip of `rows_per_item` output rows, block of `cols_per_item` output columns); the first item
+//                 of a CTA is its index, the rest are claimed from a global counter, so the grid (CTAs per SM x SMs)
+//                 balances boxes of different sizes by itself.
+//   producer    = the last warp of the CTA.  Per item it writes a header, the vertical table (per output row: the
+//                 source row that completes it, the coefficients, the output row offset) and the horizontal table
+//                 (per output column: where its taps sit in a staged row, the coefficients) into one of two item
+//                 slots, then streams the item's source rows - image and mask - through a ring of shared-memory
+//                 stages with one TMA bulk copy per row and matrix (16-byte aligned superset of the row segment, so
+//                 every DRAM sector is fetched once).  Rows above / below the crop are the clamped row: the replicated
+//                 border of cv2 costs the consumers nothing vertically.
+//   consumers   = one thread per output column.  A thread walks DOWN the source rows as they arrive: horizontal
+//                 filter of the row into registers (aligned 32-bit words, funnel shift, byte permute, DP2A), then
+//                 every output row this source row completes is emitted (vertical filter, mask, normalise, store).
+//                 Source rows are filtered once per strip and column, raw rows are dead as soon as they are filtered,
+//                 so a stage is handed back to the producer after a few rows: the ring is small (3 x ~10 KB), several
+//                 CTAs fit an SM and loads run ahead of compute.
+//
+// Bilinear: the register window is two rows (the loop is unrolled over a row pair, no data moves).  The vertical
+// pass - two separately truncated products in cv2 - runs on the FMA pipe with round-toward-minus-infinity FMAs
+// (r3_emit2), not as 32x32 high multiplies.
+// Lanczos4: the register window is a ring of eight rows indexed by (source row & 7); the table rotates the
+// coefficients instead of the data.  The replicated border left / right of the crop is written into the padding of
+// the staged rows by the warps whose columns reach it (a warp patches for itself, so no CTA-wide barrier).
 //
 // Requirements checked by the host (engine.cu: run_roi): W % 16 == 0 (the 16-byte phase of a row segment is the
-// same for every row of a crop), S even and <= 512, rows fit a stage.  Anything else takes roi_crop_kernel.
+// same for every row of a crop), cols_per_item a multiple of 32, rows fit a stage.  Anything else takes roi_crop_kernel.
 #pragma once
 #include "roi_crop.cuh"
 
@@ -38,34 +47,41 @@ struct Roi3Params {
   void* out;
   Geom g;                     // fmt 1 geometry
   int rows_per_item;          // output rows per work item (<= kR3MaxItemRows)
+  int cols_per_item;          // output columns per work item = consumer threads (multiple of 32, divides S)
+  int col_blocks;             // S / cols_per_item
   int items_per_crop;
   int n_items;
   int stage_bytes;            // multiple of 128
   int n_stages;               // <= kR3MaxStages
-  int xtab_slot;              // S * 16
-  int ring_off;               // kR3Xtab + 2 * xtab_slot, multiple of 128
+  int xtab_slot;              // cols_per_item * bytes per horizontal table entry
+  int ring_off;               // r3_xtab_off(TAPS) + 2 * xtab_slot, multiple of 128
+  unsigned int* sched;        // {next item, CTAs done}: both zero at launch, reset by the last CTA (nullptr = static round-robin)
 };
 
-constexpr int kR3MaxItemRows = 64;
+constexpr int kR3MaxItemRows = 128;
 constexpr int kR3MaxStages = 8;
 // shared-memory map (bytes)
 constexpr int kR3Full = 0;                     // mbarrier per stage: rows have landed
 constexpr int kR3Empty = 64;                   // mbarrier per stage: every consumer warp is done with the rows
-constexpr int kR3ItemFull = 128;               // mbarrier per item slot: header + vertical table written
+constexpr int kR3ItemFull = 128;               // mbarrier per item slot: header + tables written
 constexpr int kR3ItemEmpty = 144;              // mbarrier per item slot: every consumer warp is done with them
 constexpr int kR3Hdr = 192;                    // 2 x 64 B
 constexpr int kR3Ytab = 320;                   // 2 x (kR3MaxItemRows + 1) entries
 constexpr int kR3YtabEntry2 = 16;              // linear : {u_top, float b0 * 2^-20, float b1 * 2^-20, output row offset}
 constexpr int kR3YtabEntry8 = 48;              // lanczos: {u_top, output row offset, 0, 0, int coef[8] by ring slot}
-constexpr int kR3YtabSlot = (kR3MaxItemRows + 1) * kR3YtabEntry8;
-constexpr int kR3Lut = 7168;                   // 256 x u32, 1 KB aligned
-constexpr int kR3Xtab = 8192;                  // 2 x S columns x 16 B: per-column constants of the item (horizontal table);
-                                               // the ring follows at Roi3Params::ring_off
+// per kernel family (TAPS = 2 or 8): bytes of one vertical-table slot, offset of the 256 x u32 normalise table (1 KB
+// aligned) and of the horizontal table (2 x cols_per_item entries; the ring follows at Roi3Params::ring_off)
+FLOPE_HD constexpr int r3_ytab_slot(int taps) { return (kR3MaxItemRows + 1) * (taps == 8 ? kR3YtabEntry8 : kR3YtabEntry2); }
+FLOPE_HD constexpr int r3_lut_off(int taps) { return (kR3Ytab + 2 * r3_ytab_slot(taps) + 1023) & ~1023; }
+FLOPE_HD constexpr int r3_xtab_off(int taps) { return r3_lut_off(taps) + 1024; }
+constexpr int kR3XtabEntry2 = 16;              // linear : {iofs | ish << 16, a0 | a1 << 16, mofs | msel << 16, 0}
+constexpr int kR3XtabEntry8 = 32;              // lanczos: {iofs | ish << 16, mofs | msh << 16, border flags, 0, c01, c23, c45, c67}
 constexpr int kR3RingTail = 64;                // over-read of the last row's window
-static_assert(kR3Ytab + 2 * kR3YtabSlot <= kR3Lut, "item slots overlap the table");
+// staged row slot of the Lanczos4 kernel: [16 pad][image superset][32 pad][16 pad][mask superset][16 pad]
+constexpr int kR3PadL = 16, kR3PadR = 32, kR3PadM = 16;
 
 // header words
-enum { R3H_VALID = 0, R3H_CROP, R3H_UFIRST, R3H_NROWS, R3H_K, R3H_PITCH, R3H_MOFF, R3H_MISI, R3H_MISM, R3H_SW };
+enum { R3H_VALID = 0, R3H_CROP, R3H_UFIRST, R3H_NROWS, R3H_K, R3H_PITCH, R3H_XBEGIN, R3H_RGB0, R3H_MSK0, R3H_SPAN, R3H_PADS };
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t r3_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -75,6 +91,7 @@ __device__ __forceinline__ U32x4 r3_lds128(uint32_t a) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
   return v;
 }
+__device__ __forceinline__ void r3_sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void r3_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void r3_sts128(uint32_t a, U32x4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -87,7 +104,7 @@ __device__ __forceinline__ void r3_bar_expect(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a pipeline bug must trap (a visible CUDA error), never hang the box.  try_wait suspends the
-// thread for a hardware-defined interval, so the loop is not a hot spin.
+// thread until the phase completes or a time limit passes, so the loop is not a hot spin.
 __device__ __forceinline__ void r3_bar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok, spins = 0;
   for (;;) {
@@ -104,31 +121,27 @@ __device__ __forceinline__ void r3_bulk_g2s(uint32_t dst, const void* src, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-
-struct R3Col2 {             // bilinear
-  uint32_t iofs;            // byte offset (from the row slot) of the aligned word that holds the first tap byte
-  uint32_t ish;             // 8 * misalignment of the first tap byte
-  uint32_t cx;              // a0 | a1 << 16
-  uint32_t mofs;            // same for the mask row
-  uint32_t msel;            // byte-permute selector of the two mask taps
-};
-__device__ __forceinline__ R3Col2 r3_col2(int x, double scale_x, int sw, uint32_t mis_i, uint32_t moff, uint32_t mis_m) {
-  short ic[2];
-  int sx;
-  linear_coefs(x, scale_x, sw, false, sx, ic);
-  R3Col2 k;
-  k.cx = (uint32_t)(uint16_t)ic[0] | ((uint32_t)(uint16_t)ic[1] << 16);
-  const uint32_t bo = mis_i + 3u * (uint32_t)sx;
-  k.iofs = bo & ~3u;
-  k.ish = 8u * (bo & 3u);
-  const uint32_t bm = moff + mis_m + (uint32_t)sx;
-  k.mofs = bm & ~3u;
-  k.msel = (bm & 3u) | (((bm & 3u) + 1u) << 4);
-  return k;
+__device__ __forceinline__ int r3_dp2a_lo_su(uint32_t coef, uint32_t bytes, int c) {      // signed 16-bit x unsigned 8-bit
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(bytes), "r"(c));
+  return d;
 }
+__device__ __forceinline__ int r3_dp2a_hi_su(uint32_t coef, uint32_t bytes, int c) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(bytes), "r"(c));
+  return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 // producer warp
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int r3_next_item(const Roi3Params& p, int item, int lane) {
+  if (!p.sched) return item + (int)gridDim.x;
+  unsigned int v = 0;
+  if (lane == 0) v = atomicAdd(p.sched, 1u);
+  return (int)gridDim.x + (int)__shfl_sync(0xFFFFFFFFu, v, 0);
+}
+
 template <int TAPS, bool HAS_MASK>
 __device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, int lane) {
   constexpr int LO = TAPS == 8 ? 3 : 0;          // first / last tap relative to floor(source coordinate)
@@ -136,30 +149,68 @@ __device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, in
   constexpr int YE = TAPS == 8 ? kR3YtabEntry8 : kR3YtabEntry2;
   uint32_t stage = 0, sphase = 0;
   int it = 0;
-  for (int item = blockIdx.x;; item += gridDim.x) {
+  for (int item = blockIdx.x;; item = r3_next_item(p, item, lane)) {
     const int b = it & 1;
     r3_bar_wait(sb + kR3ItemEmpty + 8 * b, (((uint32_t)it >> 1) & 1u) ^ 1u);
     const uint32_t hdr = sb + kR3Hdr + 64 * b;
     if (item >= p.n_items) {
-      if (lane == 0) { r3_sts32(hdr + 4 * R3H_VALID, 0u); r3_bar_arrive(sb + kR3ItemFull + 8 * b); }
+      if (lane == 0) {
+        r3_sts32(hdr + 4 * R3H_VALID, 0u); r3_bar_arrive(sb + kR3ItemFull + 8 * b);
+        if (p.sched && atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) { p.sched[0] = 0u; p.sched[1] = 0u; __threadfence(); }
+      }
       return;
     }
-    const int crop = item / p.items_per_crop, strip = item - crop * p.items_per_crop;
+    const int crop = item / p.items_per_crop, rem = item - crop * p.items_per_crop;
+    const int strip = rem / p.col_blocks, cb = rem - strip * p.col_blocks;
     const int32_t* bx = p.boxes + (size_t)crop * 5;
     const int frame = __ldg(bx), xmin = __ldg(bx + 1), ymin = __ldg(bx + 2);
     const int sw = __ldg(bx + 3) - xmin, sh = __ldg(bx + 4) - ymin;
     if (sw <= 0 || sh <= 0) continue;            // empty box: nothing to write (the host rejects these)
     const int S = p.S;
     const int y_begin = strip * p.rows_per_item, y_end = imin(S, y_begin + p.rows_per_item);
+    const int x_begin = cb * p.cols_per_item, x_end = x_begin + p.cols_per_item;
     const int n_out = y_end - y_begin;
-    const double scale_y = axis_scale(sh, S);
+    const double scale_y = axis_scale(sh, S), scale_x = axis_scale(sw, S);
     float f;
     const int u_first = src_coord(y_begin, scale_y, f) - LO;
     const int u_last = src_coord(y_end - 1, scale_y, f) + HI;
     int n_rows = u_last - u_first + 1;
     if (TAPS == 2) n_rows = (n_rows + 1) & ~1;   // the bilinear consumers take rows in pairs
+    // ---- staged segment of a source row: columns [xc0, xc1] of the crop ----
+    const int sx_first = src_coord(x_begin, scale_x, f), sx_last = src_coord(x_end - 1, scale_x, f);
+    const int xc0 = iclamp(sx_first - LO, 0, sw - 1), xc1 = iclamp(sx_last + HI, 0, sw - 1);
+    const int span = xc1 - xc0 + 1;
+    const uint32_t pads = TAPS == 8 ? ((sx_first - LO < 0) ? 1u : 0u) | ((sx_last + HI > sw - 1) ? 2u : 0u) : 0u;
+    const uint8_t* img0 = p.frames + (long long)frame * p.frame_stride + ((long long)ymin * p.W + xmin + xc0) * 3;
+    const uint8_t* msk0 = HAS_MASK ? p.masks + (long long)frame * p.mask_stride + (long long)ymin * p.W + xmin + xc0 : nullptr;
+    const uint32_t mis_i = (uint32_t)((uintptr_t)img0 & 15), mis_m = (uint32_t)((uintptr_t)msk0 & 15);
+    const uint32_t Li = (mis_i + 3u * (uint32_t)span + 15u) & ~15u;
+    const uint32_t Lm = HAS_MASK ? (mis_m + (uint32_t)span + 15u) & ~15u : 0u;
+    const uint32_t rgb_off = TAPS == 8 ? (uint32_t)kR3PadL : 0u;                                    // slot offset of the image copy
+    const uint32_t msk_off = TAPS == 8 ? rgb_off + Li + (uint32_t)(kR3PadR + kR3PadM) : Li;         // ... of the mask copy
+    const uint32_t pitch = TAPS == 8 ? (HAS_MASK ? msk_off + Lm + (uint32_t)kR3PadM : rgb_off + Li + (uint32_t)kR3PadR) : Li + Lm;
+    const uint32_t rgb0 = rgb_off + mis_i, msk0o = msk_off + mis_m;    // slot offsets of pixel xc0
+    int K = imin(32, p.stage_bytes / (int)pitch);
+    if (TAPS == 2) K &= ~1;
+    // ---- rows: the first stage is requested before the tables are built (its latency hides behind them) ----
+    const long long rb_i = (long long)p.W * 3, rb_m = p.W;
+    auto issue = [&](int r0) {
+      const int k_this = imin(K, n_rows - r0);
+      r3_bar_wait(sb + kR3Empty + 8 * stage, sphase ^ 1u);
+      const uint32_t full = sb + kR3Full + 8 * stage;
+      if (lane == 0) r3_bar_expect(full, (uint32_t)k_this * (Li + Lm));
+      __syncwarp();
+      if (lane < k_this) {
+        const int r = iclamp(u_first + r0 + lane, 0, sh - 1);
+        const uint32_t dst = sb + (uint32_t)p.ring_off + stage * (uint32_t)p.stage_bytes + (uint32_t)lane * pitch;
+        r3_bulk_g2s(dst + rgb_off, img0 - mis_i + r * rb_i, Li, full);
+        if (HAS_MASK) r3_bulk_g2s(dst + msk_off, msk0 - mis_m + r * rb_m, Lm, full);
+      }
+      if (++stage == (uint32_t)p.n_stages) { stage = 0; sphase ^= 1u; }
+    };
+    issue(0);
     // ---- vertical table ----
-    const uint32_t ytab = sb + kR3Ytab + kR3YtabSlot * b;
+    const uint32_t ytab = sb + kR3Ytab + r3_ytab_slot(TAPS) * b;
     for (int i = lane; i <= n_out; i += 32) {
       const int y = y_begin + i;
       uint32_t ooff;
@@ -179,20 +230,21 @@ __device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, in
       } else {
         U32x4 e0, e1, e2;
         e0.y = ooff; e0.z = e0.w = 0u;
-        if (i == n_out) { e0.x = 0x7FFFFFFFu; e1.x = e1.y = e1.z = e1.w = e2.x = e2.y = e2.z = e2.w = 0u; }
+        e1.x = e1.y = e1.z = e1.w = e2.x = e2.y = e2.z = e2.w = 0u;
+        if (i == n_out) e0.x = 0x7FFFFFFFu;
         else {
           short ic[8]; int sy;
           lanczos4_coefs(y, scale_y, sy, ic);
           e0.x = (uint32_t)(sy + 4);
-          int cf[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) cf[j] = 0;
+          uint32_t cf[8];
           // ring slot k holds the source row u with (u & 7) == k; the window is u = sy - 3 + j
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int slot = (sy - 3 + j) & 7;
+          for (int k = 0; k < 8; ++k) {
+            const int j = (k - (sy - 3)) & 7;
+            int v = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) if (k == slot) cf[k] = (int)ic[j];
+            for (int jj = 0; jj < 8; ++jj) if (jj == j) v = (int)ic[jj];
+            cf[k] = (uint32_t)v;
           }
           e1.x = cf[0]; e1.y = cf[1]; e1.z = cf[2]; e1.w = cf[3];
           e2.x = cf[4]; e2.y = cf[5]; e2.z = cf[6]; e2.w = cf[7];
@@ -200,56 +252,114 @@ __device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, in
         r3_sts128(ytab + i * YE, e0); r3_sts128(ytab + i * YE + 16, e1); r3_sts128(ytab + i * YE + 32, e2);
       }
     }
-    // ---- header ----
-    const uint8_t* img0 = p.frames + (long long)frame * p.frame_stride + ((long long)ymin * p.W + xmin) * 3;
-    const uint8_t* msk0 = HAS_MASK ? p.masks + (long long)frame * p.mask_stride + (long long)ymin * p.W + xmin : nullptr;
-    const uint32_t mis_i = (uint32_t)((uintptr_t)img0 & 15), mis_m = (uint32_t)((uintptr_t)msk0 & 15);
-    const uint32_t Li = (mis_i + 3u * (uint32_t)sw + 15u) & ~15u;
-    const uint32_t Lm = HAS_MASK ? (mis_m + (uint32_t)sw + 15u) & ~15u : 0u;
-    const uint32_t pitch = Li + Lm;
-    int K = imin(32, p.stage_bytes / (int)pitch);
-    if (TAPS == 2) K &= ~1;
-    if (TAPS == 2) {
-      const double scale_x = axis_scale(sw, S);
-      for (int x = lane; x < S; x += 32) {
-        const R3Col2 k = r3_col2(x, scale_x, sw, mis_i, Li, mis_m);
+    // ---- horizontal table ----
+    for (int i = lane; i < p.cols_per_item; i += 32) {
+      const uint32_t xa = sb + r3_xtab_off(TAPS) + p.xtab_slot * b + i * (TAPS == 8 ? kR3XtabEntry8 : kR3XtabEntry2);
+      if (TAPS == 2) {
+        short ic[2]; int sx;
+        linear_coefs(x_begin + i, scale_x, sw, false, sx, ic);
+        const uint32_t bo = rgb0 + 3u * (uint32_t)(sx - xc0), bm = msk0o + (uint32_t)(sx - xc0);
         U32x4 e;
-        e.x = k.iofs | (k.ish << 16); e.y = k.cx; e.z = k.mofs | (k.msel << 16); e.w = 0u;
-        r3_sts128(sb + kR3Xtab + p.xtab_slot * b + 16 * x, e);
+        e.x = (bo & ~3u) | ((8u * (bo & 3u)) << 16);
+        e.y = (uint32_t)(uint16_t)ic[0] | ((uint32_t)(uint16_t)ic[1] << 16);
+        e.z = (bm & ~3u) | (((bm & 3u) | (((bm & 3u) + 1u) << 4)) << 16);
+        e.w = 0u;
+        r3_sts128(xa, e);
+      } else {
+        short ic[8]; int sx;
+        lanczos4_coefs(x_begin + i, scale_x, sx, ic);
+        const int rel = sx - 3 - xc0;                  // first tap relative to the first staged pixel (>= -4)
+        const uint32_t bo = (uint32_t)((int)rgb0 + 3 * rel), bm = (uint32_t)((int)msk0o + rel);
+        U32x4 e0, e1;
+        e0.x = (bo & ~3u) | ((8u * (bo & 3u)) << 16);
+        e0.y = (bm & ~3u) | ((8u * (bm & 3u)) << 16);
+        e0.z = ((pads & 1u) && rel < 0 ? 1u : 0u) | ((pads & 2u) && rel + 7 > span - 1 ? 2u : 0u);
+        e0.w = 0u;
+        e1.x = (uint32_t)(uint16_t)ic[0] | ((uint32_t)(uint16_t)ic[1] << 16);
+        e1.y = (uint32_t)(uint16_t)ic[2] | ((uint32_t)(uint16_t)ic[3] << 16);
+        e1.z = (uint32_t)(uint16_t)ic[4] | ((uint32_t)(uint16_t)ic[5] << 16);
+        e1.w = (uint32_t)(uint16_t)ic[6] | ((uint32_t)(uint16_t)ic[7] << 16);
+        r3_sts128(xa, e0); r3_sts128(xa + 16, e1);
       }
     }
     if (lane == 0) {
       r3_sts32(hdr + 4 * R3H_CROP, (uint32_t)crop); r3_sts32(hdr + 4 * R3H_UFIRST, (uint32_t)u_first);
       r3_sts32(hdr + 4 * R3H_NROWS, (uint32_t)n_rows); r3_sts32(hdr + 4 * R3H_K, (uint32_t)K);
-      r3_sts32(hdr + 4 * R3H_PITCH, pitch); r3_sts32(hdr + 4 * R3H_MOFF, Li);
-      r3_sts32(hdr + 4 * R3H_MISI, mis_i); r3_sts32(hdr + 4 * R3H_MISM, mis_m);
-      r3_sts32(hdr + 4 * R3H_SW, (uint32_t)sw); r3_sts32(hdr + 4 * R3H_VALID, 1u);
+      r3_sts32(hdr + 4 * R3H_PITCH, pitch); r3_sts32(hdr + 4 * R3H_XBEGIN, (uint32_t)x_begin);
+      r3_sts32(hdr + 4 * R3H_RGB0, rgb0); r3_sts32(hdr + 4 * R3H_MSK0, msk0o);
+      r3_sts32(hdr + 4 * R3H_SPAN, (uint32_t)span); r3_sts32(hdr + 4 * R3H_PADS, pads);
+      r3_sts32(hdr + 4 * R3H_VALID, 1u);
     }
     __syncwarp();
     if (lane == 0) r3_bar_arrive(sb + kR3ItemFull + 8 * b);
-    // ---- rows ----
-    const long long rb_i = (long long)p.W * 3, rb_m = p.W;
-    for (int r0 = 0; r0 < n_rows; r0 += K) {
-      const int k_this = imin(K, n_rows - r0);
-      r3_bar_wait(sb + kR3Empty + 8 * stage, sphase ^ 1u);
-      const uint32_t full = sb + kR3Full + 8 * stage;
-      if (lane == 0) r3_bar_expect(full, (uint32_t)k_this * pitch);
-      __syncwarp();
-      if (lane < k_this) {
-        const int r = iclamp(u_first + r0 + lane, 0, sh - 1);
-        const uint32_t dst = sb + (uint32_t)p.ring_off + stage * (uint32_t)p.stage_bytes + (uint32_t)lane * pitch;
-        r3_bulk_g2s(dst, img0 - mis_i + r * rb_i, Li, full);
-        if (HAS_MASK) r3_bulk_g2s(dst + Li, msk0 - mis_m + r * rb_m, Lm, full);
-      }
-      if (++stage == (uint32_t)p.n_stages) { stage = 0; sphase ^= 1u; }
-    }
+    for (int r0 = K; r0 < n_rows; r0 += K) issue(r0);
     ++it;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// consumers: per-column constants and the horizontal filters
+// consumers: shared pieces
 // ---------------------------------------------------------------------------------------------
+// Normalise + store one pixel.  v4 / m4 hold 4 x the cv2 result in bits 2..9 (other bits arbitrary), `base4` is the
+// value of m4's bits above bit 9 (compares run on the raw words).
+//   fmt 1: two 32-bit words [c0 c1 | c2 0] of bf16;  bf16_rn(fl(4v * fl(1/1020))) == bf16_rn(fp32(v / 255)) for all v
+//   fmt 0: three fp32 words; unmasked values come from the 256-entry table in shared memory
+// The branches are warp-uniform (votes): a warp with a partially masked pixel (mask edge) takes the general
+// quotient for every lane, everything else takes the unmasked path and zeroes its masked-out lanes with a select.
+template <bool HAS_MASK, int FMT>
+__device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, uint32_t base4, bool off, uint8_t* q,
+                                          uint32_t plane_bytes, uint32_t lut) {
+  uint32_t o[3];
+  if (HAS_MASK && __any_sync(0xFFFFFFFFu, m4 - (base4 + 4u) < 1016u)) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = __float_as_uint(normalise_u8((int)((v4[c] >> 2) & 0xFFu), (int)((m4 >> 2) & 0xFFu)));
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (FMT == 0) {
+        o[c] = r3_lds32((v4[c] & 0x3FCu) | lut);
+      } else {
+        // (float)(4v) without a conversion: the integer sits in the mantissa of 2^23 + 4v
+        uint32_t xb;
+        asm("lop3.b32 %0, %1, 0x3FC, %2, 0xEA;" : "=r"(xb) : "r"(v4[c]), "r"(0x4B000000u));
+        o[c] = __float_as_uint(fmaf(__uint_as_float(xb), 1.0f / 1020.0f, -8388608.0f * (1.0f / 1020.0f)));
+      }
+      if (FMT == 0 && HAS_MASK) o[c] = off ? 0u : o[c];
+    }
+  }
+  if (FMT == 0) {
+    *reinterpret_cast<uint32_t*>(q) = o[0];
+    *reinterpret_cast<uint32_t*>(q + plane_bytes) = o[1];
+    *reinterpret_cast<uint32_t*>(q + 2 * (size_t)plane_bytes) = o[2];
+  } else {
+    uint2 v;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(v.x) : "f"(__uint_as_float(o[1])), "f"(__uint_as_float(o[0])));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(v.y) : "f"(0.f), "f"(__uint_as_float(o[2])));
+    if (HAS_MASK) { v.x = off ? 0u : v.x; v.y = off ? 0u : v.y; }
+    *reinterpret_cast<uint2*>(q) = v;
+  }
+}
+template <int FMT>
+__device__ __forceinline__ void r3_store_zero(uint8_t* q, uint32_t plane_bytes) {
+  if (FMT == 0) {
+    *reinterpret_cast<uint32_t*>(q) = 0u;
+    *reinterpret_cast<uint32_t*>(q + plane_bytes) = 0u;
+    *reinterpret_cast<uint32_t*>(q + 2 * (size_t)plane_bytes) = 0u;
+  } else {
+    *reinterpret_cast<uint2*>(q) = make_uint2(0u, 0u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear consumer
+// ---------------------------------------------------------------------------------------------
+struct R3Col2 {
+  uint32_t iofs;            // byte offset (from the row slot) of the aligned word that holds the first tap byte
+  uint32_t ish;             // 8 * misalignment of the first tap byte
+  uint32_t cx;              // a0 | a1 << 16
+  uint32_t mofs;            // same for the mask row
+  uint32_t msel;            // byte-permute selector of the two mask taps
+};
 // Horizontally filtered source row for cv2's vertical pass, which consumes A = S >> 4 (S = a0 * p0 + a1 * p1 < 2^20).
 // The vertical pass runs on the FMA pipe (see r3_emit2), so the value is kept as the float 2^23 + 16 * A: its bit
 // pattern is 0x4B000000 | (S & ~15), one logic operation on the DP2A result.
@@ -274,17 +384,11 @@ __device__ __forceinline__ void r3_hfilt2(uint32_t row, const R3Col2& k, uint32_
     dst[HAS_MASK ? 3 : 0] = r3_f16a(__dp2a_lo(k.cx, r3, 0u));
   }
 }
-
 // One output pixel.  cv2's vertical pass is ((b0 * A0 >> 16) + (b1 * A1 >> 16) + 2) >> 2 with two separate truncations.
 // Both happen on the FMA pipe: with F = 2^23 + 16 A (r3_hfilt2), bf = b * 2^-20 and round-toward-minus-infinity,
 //   fma.rm(bf0, F0, M0)          = M0 + 8 b0 + floor(b0 A0 / 65536)              (exact: one rounding, ulp 1 in [2^23, 2^24))
 //   fma.rm(bf1, F1, the above)   = M0 + 8 (b0 + b1) + floor(..) + floor(..)
 // so M0 = 1.5 * 2^23 + 2 - 8 (b0 + b1) leaves the bit pattern 0x4B400000 + v4, v4 = 4 x the cv2 result + (0..3).
-//   fmt 1: two 32-bit words [c0 c1 | c2 0] of bf16;  bf16_rn(fl(4v * fl(1/1020))) == bf16_rn(fp32(v / 255)) for all v
-//   fmt 0: three fp32 words; unmasked values come from the 256-entry table in shared memory
-// The branches are warp-uniform (votes): a warp whose 32 pixels are all masked out skips the image channels, a warp
-// with a partially masked pixel (mask edge) takes the general quotient for every lane, everything else takes the
-// unmasked path and zeroes its masked-out lanes with a select.
 __device__ __forceinline__ float r3_fma_rm(float a, float b, float c) {
   float d;
   asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -297,96 +401,56 @@ __device__ __forceinline__ void r3_emit2(const uint32_t (&lo)[HAS_MASK ? 4 : 3],
   constexpr uint32_t kBase = 0x4B400000u;    // 1.5 * 2^23
   const float b0 = __uint_as_float(yt.y), b1 = __uint_as_float(yt.z);
   const float m0 = fmaf(b0 + b1, -8388608.0f, 12582914.0f);
-  uint32_t o[3];
   uint32_t m4 = kBase + 1020u;
   if (HAS_MASK) m4 = __float_as_uint(r3_fma_rm(b1, __uint_as_float(up[NCH - 1]), r3_fma_rm(b0, __uint_as_float(lo[NCH - 1]), m0)));
   const bool off = HAS_MASK && m4 < kBase + 4u;      // masked out: exactly zero whatever the image holds
   if (HAS_MASK && !__any_sync(0xFFFFFFFFu, !off)) {
-    o[0] = o[1] = o[2] = 0u;
+    r3_store_zero<FMT>(out + yt.w, plane_bytes);
   } else {
     uint32_t v4[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) v4[j] = __float_as_uint(r3_fma_rm(b1, __uint_as_float(up[j]), r3_fma_rm(b0, __uint_as_float(lo[j]), m0)));
-    if (HAS_MASK && __any_sync(0xFFFFFFFFu, m4 - (kBase + 4u) < 1016u)) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) o[c] = __float_as_uint(normalise_u8((int)((v4[c] >> 2) & 0xFFu), (int)((m4 >> 2) & 0xFFu)));
-    } else {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (FMT == 0) {
-          o[c] = r3_lds32((v4[c] & 0x3FCu) | lut);
-        } else {
-          // (float)(4v) without a conversion: the integer sits in the mantissa of 2^23 + 4v
-          uint32_t xb;
-          asm("lop3.b32 %0, %1, 0x3FC, %2, 0xEA;" : "=r"(xb) : "r"(v4[c]), "r"(0x4B000000u));
-          o[c] = __float_as_uint(fmaf(__uint_as_float(xb), 1.0f / 1020.0f, -8388608.0f * (1.0f / 1020.0f)));
-        }
-        if (FMT == 0 && HAS_MASK) o[c] = off ? 0u : o[c];
-      }
-    }
-  }
-  if (FMT == 0) {
-    uint8_t* q = out + yt.w;
-    *reinterpret_cast<uint32_t*>(q) = o[0];
-    *reinterpret_cast<uint32_t*>(q + plane_bytes) = o[1];
-    *reinterpret_cast<uint32_t*>(q + 2 * (size_t)plane_bytes) = o[2];
-  } else {
-    uint2 v;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(v.x) : "f"(__uint_as_float(o[1])), "f"(__uint_as_float(o[0])));
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(v.y) : "f"(0.f), "f"(__uint_as_float(o[2])));
-    if (HAS_MASK) { v.x = off ? 0u : v.x; v.y = off ? 0u : v.y; }
-    *reinterpret_cast<uint2*>(out + yt.w) = v;
+    r3_finish<HAS_MASK, FMT>(v4, m4, kBase, off, out + yt.w, plane_bytes, lut);
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// bilinear consumer
-// ---------------------------------------------------------------------------------------------
-template <bool HAS_MASK, int FMT, int NCOL>
+template <bool HAS_MASK, int FMT>
 __device__ __forceinline__ void r3_consumer2(const Roi3Params& p, uint32_t sb, int t, int lane) {
-  constexpr int NCH = HAS_MASK ? 4 : 3;
+  constexpr int NCH = HAS_MASK ? 4 : 3, TAPS = 2;
   const int S = p.S;
-  const uint32_t lut = sb + kR3Lut;
-  const uint32_t ring_end = sb + (uint32_t)p.ring_off + (uint32_t)p.n_stages * (uint32_t)p.stage_bytes;
+  const uint32_t lut = sb + r3_lut_off(TAPS);
+  const uint32_t ring = sb + (uint32_t)p.ring_off;
   const uint32_t bars_end = sb + kR3Full + 8u * (uint32_t)p.n_stages;
-  uint32_t stage_row = sb + (uint32_t)p.ring_off, full = sb + kR3Full, sphase = 0;    // ring position; `empty` sits kR3Empty behind `full`
-  uint8_t* out0[NCOL];
+  uint32_t stage_row = ring, full = sb + kR3Full, sphase = 0;    // ring position; `empty` sits kR3Empty behind `full`
+  uint8_t* out0;
   uint32_t plane_bytes = 0u;
-#pragma unroll
-  for (int c = 0; c < NCOL; ++c) {
-    const int x = t + c * (S / NCOL);
-    if (FMT == 0) {
-      out0[c] = reinterpret_cast<uint8_t*>(p.out) + (long long)x * 4;
-      plane_bytes = (uint32_t)S * (uint32_t)S * 4u;
-    } else {
-      out0[c] = reinterpret_cast<uint8_t*>(p.out) + (long long)p.g.base * 16 + (long long)(x >> 1) * 16 + (x & 1) * 8;
-    }
+  if (FMT == 0) {
+    out0 = reinterpret_cast<uint8_t*>(p.out) + (long long)t * 4;
+    plane_bytes = (uint32_t)S * (uint32_t)S * 4u;
+  } else {
+    out0 = reinterpret_cast<uint8_t*>(p.out) + (long long)p.g.base * 16 + (long long)t * 8;   // (x >> 1) * 16 + (x & 1) * 8 == x * 8
   }
   const long long crop_bytes = FMT == 0 ? 3LL * S * S * 4 : (long long)p.g.Hp * p.g.Wp * 16;
+  const int col_bytes = FMT == 0 ? 4 : 8;
   for (int it = 0;; ++it) {
     const int b = it & 1;
     r3_bar_wait(sb + kR3ItemFull + 8 * b, ((uint32_t)it >> 1) & 1u);
     const uint32_t hdr = sb + kR3Hdr + 64 * b;
     const U32x4 h0 = r3_lds128(hdr), h1 = r3_lds128(hdr + 16);
     if (h0.x == 0u) return;
-    const int crop = (int)h0.y;
     int u = (int)h0.z, rows_left = (int)h0.w;
     const int K = (int)h1.x;
     const uint32_t pitch = h1.y;
-    R3Col2 col[NCOL];
-    uint8_t* out[NCOL];
-#pragma unroll
-    for (int c = 0; c < NCOL; ++c) {
-      const U32x4 e = r3_lds128(sb + kR3Xtab + p.xtab_slot * b + 16 * (t + c * (S / NCOL)));
-      col[c].iofs = e.x & 0xFFFFu; col[c].ish = e.x >> 16; col[c].cx = e.y; col[c].mofs = e.z & 0xFFFFu; col[c].msel = e.z >> 16;
-      out[c] = out0[c] + crop * crop_bytes;
+    R3Col2 col;
+    {
+      const U32x4 e = r3_lds128(sb + r3_xtab_off(TAPS) + p.xtab_slot * b + kR3XtabEntry2 * t);
+      col.iofs = e.x & 0xFFFFu; col.ish = e.x >> 16; col.cx = e.y; col.mofs = e.z & 0xFFFFu; col.msel = e.z >> 16;
     }
-    uint32_t A[NCOL][NCH], B[NCOL][NCH];
+    uint8_t* out = out0 + (int)h0.y * crop_bytes + (int)h1.z * col_bytes;
+    uint32_t A[NCH], B[NCH];
 #pragma unroll
-    for (int c = 0; c < NCOL; ++c)
-#pragma unroll
-      for (int j = 0; j < NCH; ++j) A[c][j] = B[c][j] = 0u;
-    uint32_t ya = sb + kR3Ytab + kR3YtabSlot * b;
+    for (int j = 0; j < NCH; ++j) A[j] = B[j] = 0u;
+    uint32_t ya = sb + kR3Ytab + r3_ytab_slot(TAPS) * b;
     U32x4 yt = r3_lds128(ya);
     while (rows_left > 0) {
       const int k_this = imin(K, rows_left);
@@ -394,20 +458,16 @@ __device__ __forceinline__ void r3_consumer2(const Roi3Params& p, uint32_t sb, i
       r3_bar_wait(full, sphase);
       uint32_t row = stage_row;
       for (int k = 0; k < k_this; k += 2) {
-#pragma unroll
-        for (int c = 0; c < NCOL; ++c) r3_hfilt2<HAS_MASK>(row, col[c], A[c]);
+        r3_hfilt2<HAS_MASK>(row, col, A);
         while ((int)yt.x == u) {             // output rows whose upper source row is u
-#pragma unroll
-          for (int c = 0; c < NCOL; ++c) r3_emit2<HAS_MASK, FMT>(B[c], A[c], yt, out[c], plane_bytes, lut);
+          r3_emit2<HAS_MASK, FMT>(B, A, yt, out, plane_bytes, lut);
           ya += kR3YtabEntry2;
           yt = r3_lds128(ya);
         }
         ++u; row += pitch;
-#pragma unroll
-        for (int c = 0; c < NCOL; ++c) r3_hfilt2<HAS_MASK>(row, col[c], B[c]);
+        r3_hfilt2<HAS_MASK>(row, col, B);
         while ((int)yt.x == u) {
-#pragma unroll
-          for (int c = 0; c < NCOL; ++c) r3_emit2<HAS_MASK, FMT>(A[c], B[c], yt, out[c], plane_bytes, lut);
+          r3_emit2<HAS_MASK, FMT>(A, B, yt, out, plane_bytes, lut);
           ya += kR3YtabEntry2;
           yt = r3_lds128(ya);
         }
@@ -416,7 +476,7 @@ __device__ __forceinline__ void r3_consumer2(const Roi3Params& p, uint32_t sb, i
       __syncwarp();
       if (lane == 0) r3_bar_arrive(full + kR3Empty);
       stage_row += (uint32_t)p.stage_bytes; full += 8u;
-      if (full == bars_end) { stage_row = sb + (uint32_t)p.ring_off; full = sb + kR3Full; sphase ^= 1u; }
+      if (full == bars_end) { stage_row = ring; full = sb + kR3Full; sphase ^= 1u; }
     }
     __syncwarp();
     if (lane == 0) r3_bar_arrive(sb + kR3ItemEmpty + 8 * b);
@@ -424,10 +484,173 @@ __device__ __forceinline__ void r3_consumer2(const Roi3Params& p, uint32_t sb, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel: blockDim = 32 * (consumer warps + 1); consumer thread t owns output columns t + c * S / NCOL
+// Lanczos4 consumer
 // ---------------------------------------------------------------------------------------------
-template <int TAPS, bool HAS_MASK, int FMT, int NCOL>
-__global__ void __launch_bounds__(NCOL == 1 ? 256 : 288) roi3_kernel(const __grid_constant__ Roi3Params p) {
+struct R3Col8 {
+  uint32_t iofs, ish, mofs, msh;
+  uint32_t c01, c23, c45, c67;
+};
+template <bool HAS_MASK>
+__device__ __forceinline__ void r3_hfilt8(uint32_t row, const R3Col8& k, int (&dst)[HAS_MASK ? 4 : 3]) {
+  const uint32_t wa = row + k.iofs;
+  uint32_t u[6];
+  {
+    uint32_t wv[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) wv[i] = r3_lds32(wa + 4 * i);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) u[i] = __funnelshift_r(wv[i], wv[i + 1], k.ish);   // bytes 0..23 = 8 pixels x 3 channels
+  }
+  int a0, a1, a2;
+  uint32_t r;
+  r = __byte_perm(u[0], u[1], 0x4130); a0 = r3_dp2a_lo_su(k.c01, r, 0); a1 = r3_dp2a_hi_su(k.c01, r, 0);     // taps 0,1: bytes (0,3) (1,4)
+  r = __byte_perm(u[0], u[1], 0x0052); a2 = r3_dp2a_lo_su(k.c01, r, 0);                                      //           bytes (2,5)
+  r = __byte_perm(u[1], u[2], 0x6352); a0 = r3_dp2a_lo_su(k.c23, r, a0); a1 = r3_dp2a_hi_su(k.c23, r, a1);   // taps 2,3: bytes (6,9) (7,10)
+  r = __byte_perm(u[1], u[2], 0x0074); a2 = r3_dp2a_lo_su(k.c23, r, a2);                                     //           bytes (8,11)
+  r = __byte_perm(u[3], u[4], 0x4130); a0 = r3_dp2a_lo_su(k.c45, r, a0); a1 = r3_dp2a_hi_su(k.c45, r, a1);   // taps 4,5: bytes (12,15) (13,16)
+  r = __byte_perm(u[3], u[4], 0x0052); a2 = r3_dp2a_lo_su(k.c45, r, a2);
+  r = __byte_perm(u[4], u[5], 0x6352); a0 = r3_dp2a_lo_su(k.c67, r, a0); a1 = r3_dp2a_hi_su(k.c67, r, a1);   // taps 6,7: bytes (18,21) (19,22)
+  r = __byte_perm(u[4], u[5], 0x0074); a2 = r3_dp2a_lo_su(k.c67, r, a2);
+  dst[0] = a0; dst[1] = a1; dst[2] = a2;
+  if (HAS_MASK) {
+    const uint32_t ma = row + k.mofs;
+    const uint32_t m0 = r3_lds32(ma), m1 = r3_lds32(ma + 4), m2 = r3_lds32(ma + 8);
+    const uint32_t t0 = __funnelshift_r(m0, m1, k.msh), t1 = __funnelshift_r(m1, m2, k.msh);
+    int a3 = r3_dp2a_lo_su(k.c01, t0, 0);
+    a3 = r3_dp2a_hi_su(k.c23, t0, a3);
+    a3 = r3_dp2a_lo_su(k.c45, t1, a3);
+    a3 = r3_dp2a_hi_su(k.c67, t1, a3);
+    dst[HAS_MASK ? 3 : 0] = a3;
+  }
+}
+// replicated border of the crop: 4 pixels in front of / behind the staged segment of every row of a stage
+template <bool HAS_MASK>
+__device__ __forceinline__ void r3_patch8(uint32_t stage_row, int k_this, uint32_t pitch, uint32_t rgb0, uint32_t msk0, int span,
+                                          bool left, bool right, int lane) {
+  for (int i = lane; i < 4 * k_this; i += 32) {
+    const uint32_t rowa = stage_row + (uint32_t)(i >> 2) * pitch;
+    const int j = (i & 3) + 1;
+    if (left) {
+      const uint32_t px = rowa + rgb0;
+      const uint32_t c0 = r3_lds8(px), c1 = r3_lds8(px + 1), c2 = r3_lds8(px + 2);
+      r3_sts8(px - 3 * j, c0); r3_sts8(px - 3 * j + 1, c1); r3_sts8(px - 3 * j + 2, c2);
+      if (HAS_MASK) r3_sts8(rowa + msk0 - j, r3_lds8(rowa + msk0));
+    }
+    if (right) {
+      const uint32_t px = rowa + rgb0 + 3u * (uint32_t)(span - 1);
+      const uint32_t c0 = r3_lds8(px), c1 = r3_lds8(px + 1), c2 = r3_lds8(px + 2);
+      r3_sts8(px + 3 * j, c0); r3_sts8(px + 3 * j + 1, c1); r3_sts8(px + 3 * j + 2, c2);
+      if (HAS_MASK) r3_sts8(rowa + msk0 + (uint32_t)(span - 1 + j), r3_lds8(rowa + msk0 + (uint32_t)(span - 1)));
+    }
+  }
+}
+
+template <bool HAS_MASK, int FMT>
+__device__ __forceinline__ void r3_consumer8(const Roi3Params& p, uint32_t sb, int t, int lane) {
+  constexpr int NCH = HAS_MASK ? 4 : 3, TAPS = 8;
+  const int S = p.S;
+  const uint32_t lut = sb + r3_lut_off(TAPS);
+  const uint32_t ring = sb + (uint32_t)p.ring_off;
+  const uint32_t bars_end = sb + kR3Full + 8u * (uint32_t)p.n_stages;
+  uint32_t stage_row = ring, full = sb + kR3Full, sphase = 0;
+  uint8_t* out0;
+  uint32_t plane_bytes = 0u;
+  if (FMT == 0) {
+    out0 = reinterpret_cast<uint8_t*>(p.out) + (long long)t * 4;
+    plane_bytes = (uint32_t)S * (uint32_t)S * 4u;
+  } else {
+    out0 = reinterpret_cast<uint8_t*>(p.out) + (long long)p.g.base * 16 + (long long)t * 8;
+  }
+  const long long crop_bytes = FMT == 0 ? 3LL * S * S * 4 : (long long)p.g.Hp * p.g.Wp * 16;
+  const int col_bytes = FMT == 0 ? 4 : 8;
+  for (int it = 0;; ++it) {
+    const int b = it & 1;
+    r3_bar_wait(sb + kR3ItemFull + 8 * b, ((uint32_t)it >> 1) & 1u);
+    const uint32_t hdr = sb + kR3Hdr + 64 * b;
+    const U32x4 h0 = r3_lds128(hdr), h1 = r3_lds128(hdr + 16), h2 = r3_lds128(hdr + 32);
+    if (h0.x == 0u) return;
+    int u = (int)h0.z, rows_left = (int)h0.w;
+    const int K = (int)h1.x;
+    const uint32_t pitch = h1.y, rgb0 = h1.w, msk0 = h2.x;
+    const int span = (int)h2.y;
+    R3Col8 col;
+    bool patch_l, patch_r;
+    {
+      const uint32_t xa = sb + r3_xtab_off(TAPS) + p.xtab_slot * b + kR3XtabEntry8 * t;
+      const U32x4 e0 = r3_lds128(xa), e1 = r3_lds128(xa + 16);
+      col.iofs = e0.x & 0xFFFFu; col.ish = e0.x >> 16; col.mofs = e0.y & 0xFFFFu; col.msh = e0.y >> 16;
+      col.c01 = e1.x; col.c23 = e1.y; col.c45 = e1.z; col.c67 = e1.w;
+      patch_l = __any_sync(0xFFFFFFFFu, e0.z & 1u);
+      patch_r = __any_sync(0xFFFFFFFFu, e0.z & 2u);
+    }
+    uint8_t* out = out0 + (int)h0.y * crop_bytes + (int)h1.z * col_bytes;
+    int R[8][NCH];                           // ring: slot (u & 7) holds filtered source row u
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) R[i][j] = 0;
+    uint32_t ya = sb + kR3Ytab + r3_ytab_slot(TAPS) * b;
+    U32x4 yt = r3_lds128(ya);
+    while (rows_left > 0) {
+      const int k_this = imin(K, rows_left);
+      rows_left -= k_this;
+      r3_bar_wait(full, sphase);
+      if (patch_l || patch_r) {
+        r3_patch8<HAS_MASK>(stage_row, k_this, pitch, rgb0, msk0, span, patch_l, patch_r, lane);
+        __syncwarp();
+      }
+      uint32_t row = stage_row;
+      for (int k = 0; k < k_this; ++k, ++u, row += pitch) {
+        switch (u & 7) {
+          case 0: r3_hfilt8<HAS_MASK>(row, col, R[0]); break;
+          case 1: r3_hfilt8<HAS_MASK>(row, col, R[1]); break;
+          case 2: r3_hfilt8<HAS_MASK>(row, col, R[2]); break;
+          case 3: r3_hfilt8<HAS_MASK>(row, col, R[3]); break;
+          case 4: r3_hfilt8<HAS_MASK>(row, col, R[4]); break;
+          case 5: r3_hfilt8<HAS_MASK>(row, col, R[5]); break;
+          case 6: r3_hfilt8<HAS_MASK>(row, col, R[6]); break;
+          default: r3_hfilt8<HAS_MASK>(row, col, R[7]); break;
+        }
+        while ((int)yt.x == u) {             // output rows whose last source row is u
+          const U32x4 ca = r3_lds128(ya + 16), cb = r3_lds128(ya + 32);
+          const int cf[8] = {(int)ca.x, (int)ca.y, (int)ca.z, (int)ca.w, (int)cb.x, (int)cb.y, (int)cb.z, (int)cb.w};
+          // 4 x the cv2 result, clamped: ((acc + 2^21) >> 22 clamped to 0..255) * 4 == ((acc + 2^21) >> 20 clamped to 0..1023) & 0x3FC
+          auto vpass = [&](int j) {
+            int acc = 1 << 21;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc += R[i][j] * cf[i];
+            return (uint32_t)iclamp(acc >> 20, 0, 1023);
+          };
+          const uint32_t m4 = HAS_MASK ? vpass(NCH - 1) : 1020u;
+          const bool off = HAS_MASK && m4 < 4u;
+          uint8_t* q = out + yt.y;
+          if (HAS_MASK && !__any_sync(0xFFFFFFFFu, !off)) {
+            r3_store_zero<FMT>(q, plane_bytes);
+          } else {
+            uint32_t v4[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) v4[j] = vpass(j);
+            r3_finish<HAS_MASK, FMT>(v4, m4, 0u, off, q, plane_bytes, lut);
+          }
+          ya += kR3YtabEntry8;
+          yt = r3_lds128(ya);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) r3_bar_arrive(full + kR3Empty);
+      stage_row += (uint32_t)p.stage_bytes; full += 8u;
+      if (full == bars_end) { stage_row = ring; full = sb + kR3Full; sphase ^= 1u; }
+    }
+    __syncwarp();
+    if (lane == 0) r3_bar_arrive(sb + kR3ItemEmpty + 8 * b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel: blockDim = cols_per_item + 32; consumer thread t owns output column x_begin + t of the item
+// ---------------------------------------------------------------------------------------------
+template <int TAPS, bool HAS_MASK, int FMT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) roi3_kernel(const __grid_constant__ Roi3Params p) {
   extern __shared__ __align__(1024) uint8_t r3_smem[];
   const uint32_t sb = smem_u32(r3_smem);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -438,13 +661,11 @@ __global__ void __launch_bounds__(NCOL == 1 ? 256 : 288) roi3_kernel(const __gri
     for (int b = 0; b < 2; ++b) { r3_bar_init(sb + kR3ItemFull + 8 * b, 1u); r3_bar_init(sb + kR3ItemEmpty + 8 * b, (uint32_t)n_cons); }
     mbar_fence_init();
   }
-  if (FMT == 0) for (int i = t; i < 256; i += blockDim.x) r3_sts32(sb + kR3Lut + 4 * i, f32_bits(normalise_u8(i, 255)));
+  if (FMT == 0) for (int i = t; i < 256; i += blockDim.x) r3_sts32(sb + r3_lut_off(TAPS) + 4 * i, f32_bits(normalise_u8(i, 255)));
   __syncthreads();
-  if (warp == n_cons) {
-    r3_producer<TAPS, HAS_MASK>(p, sb, lane);
-  } else if (t < p.S / NCOL) {
-    r3_consumer2<HAS_MASK, FMT, NCOL>(p, sb, t, lane);
-  }
+  if (warp == n_cons) r3_producer<TAPS, HAS_MASK>(p, sb, lane);
+  else if (TAPS == 8) r3_consumer8<HAS_MASK, FMT>(p, sb, t, lane);
+  else r3_consumer2<HAS_MASK, FMT>(p, sb, t, lane);
 }
 #endif  // __CUDACC__
 

@@ -43,15 +43,15 @@ def report(tag, ms, byts, nn):
 eng = _lib.Engine(0, max_batch=n, crop_hw=224)
 by_m = float((4 * side ** 2 + 301056 + 20).sum())
 by_n = float((3 * side ** 2 + 301056 + 20).sum())
-scfgs = [(28, 10, 3, 0)] if quick else [(28, 10, 3, 0), (32, 10, 3, 0), (56, 10, 3, 0), (16, 10, 3, 0), (28, 6, 4, 0), (28, 16, 3, 0),
-                                        (28, 10, 2, 0), (28, 10, 3, 4), (28, 10, 3, 3), (112, 10, 3, 0)]
-for rows, kb, stages, per_sm in scfgs:
+scfgs = [(28, 10, 3, 0, 1)] if quick else [(28, 10, 3, 0, 1), (28, 10, 3, 0, 0), (16, 10, 3, 0, 1), (14, 10, 3, 0, 1), (56, 10, 3, 0, 1),
+                                           (28, 6, 4, 0, 1), (28, 8, 3, 0, 1), (28, 10, 3, 3, 1), (28, 10, 3, 5, 1), (28, 6, 3, 5, 1), (28, 6, 3, 6, 1)]
+for rows, kb, stages, per_sm, dyn in scfgs:
     eng.debug_set("roi_item_rows", rows); eng.debug_set("roi_stage_kb", kb); eng.debug_set("roi_stages", stages)
-    eng.debug_set("roi_ctas_per_sm", per_sm)
+    eng.debug_set("roi_ctas_per_sm", per_sm); eng.debug_set("roi_dynamic", dyn)
     for mask_on in (True, False):
         m = mk if mask_on else None
         ms = timeit(lambda: eng.roi_crop(fr, m, bx, 224, _lib.INTERP_LINEAR, out_fmt=_lib.OUT_ENGINE))
-        report(f"stream rows={rows} kb={kb} stages={stages} per_sm={per_sm} bilinear->224 bf16 engine mask={int(mask_on)}", ms,
+        report(f"stream rows={rows} kb={kb} stages={stages} per_sm={per_sm} dyn={dyn} bilinear->224 bf16 engine mask={int(mask_on)}", ms,
                by_m if mask_on else by_n, n)
 eng.debug_set("roi_stream", 0)
 eng.debug_set("roi_staged", 0)
@@ -76,6 +76,13 @@ s = side[:nb]
 byts = float((4 * s ** 2 + 3145728 + 20).sum())
 ms = timeit(lambda: eng.roi_crop(fr, mk, bx[:nb], 512, _lib.INTERP_LINEAR, out=out), reps=5)
 report("stream bilinear->512 f32 NCHW mask=1", ms, byts, nb)
+for rows, kb, stages in ([(128, 10, 3)] if quick else [(128, 10, 3), (64, 10, 3), (128, 16, 3), (128, 6, 4), (86, 10, 3)]):
+    eng.debug_set("roi_item_rows8", rows); eng.debug_set("roi_stage_kb", kb); eng.debug_set("roi_stages", stages)
+    for mask_on in (True, False):
+        ms = timeit(lambda: eng.roi_crop(fr, mk if mask_on else None, bx[:nb], 512, _lib.INTERP_LANCZOS4, out=out), reps=5)
+        report(f"stream rows={rows} kb={kb} stages={stages} lanczos4->512 f32 NCHW mask={int(mask_on)}", ms,
+               byts if mask_on else float((3 * s ** 2 + 3145728 + 20).sum()), nb)
+eng.debug_set("roi_stage_kb", 10); eng.debug_set("roi_stages", 3)
 eng.debug_set("roi_stream", 0)
 eng.debug_set("roi_staged", 0)
 for interp, name in ((_lib.INTERP_LANCZOS4, "lanczos4"), (_lib.INTERP_LINEAR, "bilinear")):
