@@ -176,7 +176,7 @@ struct flope_engine {
   std::vector<ConvLayer> layers;
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
   int roi_stream = 1;                            // streaming ROI kernels (roi3_kernel, roi_stream.cuh): the production path
-  int roi_item_rows = 28;                        // output rows per work item of the streaming bilinear kernel
+  int roi_item_rows = 56;                        // output rows per work item of the streaming bilinear kernel
   int roi_item_rows8 = 128;                       // same for the streaming Lanczos4 kernel
   int roi_stage_kb = 10;                         // bytes per ring stage of the streaming kernels
   int roi_stages = 3;                            // ring depth

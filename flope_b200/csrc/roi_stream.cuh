@@ -304,7 +304,7 @@ __device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, in
 // value of m4's bits above bit 9 (compares run on the raw words).
 //   fmt 1: two 32-bit words [c0 c1 | c2 0] of bf16;  bf16_rn(fl(4v * fl(1/1020))) == bf16_rn(fp32(v / 255)) for all v
 //   fmt 0: three fp32 words; unmasked values come from the 256-entry table in shared memory
-// The branches are warp-uniform (votes): a warp with a partially masked pixel (mask edge) takes the general
+// The branch is warp-uniform (a vote): a warp with a partially masked pixel (mask edge) takes the general
 // quotient for every lane, everything else takes the unmasked path and zeroes its masked-out lanes with a select.
 template <bool HAS_MASK, int FMT>
 __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, uint32_t base4, bool off, uint8_t* q,
@@ -339,17 +339,6 @@ __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, 
     *reinterpret_cast<uint2*>(q) = v;
   }
 }
-template <int FMT>
-__device__ __forceinline__ void r3_store_zero(uint8_t* q, uint32_t plane_bytes) {
-  if (FMT == 0) {
-    *reinterpret_cast<uint32_t*>(q) = 0u;
-    *reinterpret_cast<uint32_t*>(q + plane_bytes) = 0u;
-    *reinterpret_cast<uint32_t*>(q + 2 * (size_t)plane_bytes) = 0u;
-  } else {
-    *reinterpret_cast<uint2*>(q) = make_uint2(0u, 0u);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // bilinear consumer
 // ---------------------------------------------------------------------------------------------
@@ -404,14 +393,12 @@ __device__ __forceinline__ void r3_emit2(const uint32_t (&lo)[HAS_MASK ? 4 : 3],
   uint32_t m4 = kBase + 1020u;
   if (HAS_MASK) m4 = __float_as_uint(r3_fma_rm(b1, __uint_as_float(up[NCH - 1]), r3_fma_rm(b0, __uint_as_float(lo[NCH - 1]), m0)));
   const bool off = HAS_MASK && m4 < kBase + 4u;      // masked out: exactly zero whatever the image holds
-  if (HAS_MASK && !__any_sync(0xFFFFFFFFu, !off)) {
-    r3_store_zero<FMT>(out + yt.w, plane_bytes);
-  } else {
-    uint32_t v4[3];
+  // (No shortcut for warps whose 32 pixels are all masked out: the warps of a CTA advance stage by stage together, so
+  //  the time of a strip is the time of its busiest warp and the vote would only add instructions to that one.)
+  uint32_t v4[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) v4[j] = __float_as_uint(r3_fma_rm(b1, __uint_as_float(up[j]), r3_fma_rm(b0, __uint_as_float(lo[j]), m0)));
-    r3_finish<HAS_MASK, FMT>(v4, m4, kBase, off, out + yt.w, plane_bytes, lut);
-  }
+  for (int j = 0; j < 3; ++j) v4[j] = __float_as_uint(r3_fma_rm(b1, __uint_as_float(up[j]), r3_fma_rm(b0, __uint_as_float(lo[j]), m0)));
+  r3_finish<HAS_MASK, FMT>(v4, m4, kBase, off, out + yt.w, plane_bytes, lut);
 }
 
 template <bool HAS_MASK, int FMT>
@@ -624,14 +611,10 @@ __device__ __forceinline__ void r3_consumer8(const Roi3Params& p, uint32_t sb, i
           const uint32_t m4 = HAS_MASK ? vpass(NCH - 1) : 1020u;
           const bool off = HAS_MASK && m4 < 4u;
           uint8_t* q = out + yt.y;
-          if (HAS_MASK && !__any_sync(0xFFFFFFFFu, !off)) {
-            r3_store_zero<FMT>(q, plane_bytes);
-          } else {
-            uint32_t v4[3];
+          uint32_t v4[3];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) v4[j] = vpass(j);
-            r3_finish<HAS_MASK, FMT>(v4, m4, 0u, off, q, plane_bytes, lut);
-          }
+          for (int j = 0; j < 3; ++j) v4[j] = vpass(j);
+          r3_finish<HAS_MASK, FMT>(v4, m4, 0u, off, q, plane_bytes, lut);
           ya += kR3YtabEntry8;
           yt = r3_lds128(ya);
         }

@@ -37,8 +37,8 @@ def run(m):
 
 
 for rows, kb, stages, per_sm, dyn in cfgs:
-    eng.debug_set("roi_item_rows8" if lanczos else "roi_item_rows", rows); eng.debug_set("roi_stage_kb", kb)
-    eng.debug_set("roi_stages", stages); eng.debug_set("roi_ctas_per_sm", per_sm); eng.debug_set("roi_dynamic", dyn)
+    eng.debug_set("roi_item_rows8" if lanczos else "roi_item_rows", rows); eng.debug_set("roi_stage_kb", kb); eng.debug_set("roi_stages", stages)
+    eng.debug_set("roi_ctas_per_sm", per_sm); eng.debug_set("roi_dynamic", dyn)
     for mask_on in (True, False):
         m = mk if mask_on else None
         for _ in range(3):
