@@ -181,12 +181,6 @@ struct flope_engine {
   int roi_stage_kb = 10;                         // bytes per ring stage of the streaming kernels
   int roi_stages = 3;                            // ring depth
   int roi_ctas_per_sm = 0;                       // 0 = as many as fit
-  bool roi_staged = true;                        // staged ROI kernels (roi2_kernel); 0 = generic one-thread-per-column kernel
-  int roi_strip = 32;                            // output rows per CTA of the staged bilinear ROI kernel
-  int roi_sub = 2;                               // sub-strips per CTA of the staged bilinear ROI kernel
-  int roi_strip8 = 128;                          // output rows per CTA of the staged Lanczos4 ROI kernel
-  int roi_data_kb = 36;                          // staging area of the staged ROI kernels
-  int roi_lut = 1;                               // unmasked pixels: 1 = shared-memory table, 0 = arithmetic
   bool chain_coop = false;                       // launch chains cooperatively (gang-scheduled): needed when several engines share a device
   unsigned long long* d_stamps = nullptr;        // phase stamps of the conv launches of one forward ("timeline" debug option)
   int stamp_launch = 0;
@@ -794,21 +788,6 @@ int run_head(flope_engine* e, const float* feat, const float* r9_in, const float
   return FLOPE_OK;
 }
 
-// shared memory of the staged ROI kernels: tables + staging area (see roi_crop.cuh)
-template <int TAPS, bool HAS_MASK, int FMT, bool LUT>
-cudaError_t roi2_launch(const RoiParams& rp, dim3 grid, int block, size_t smem, cudaStream_t st) {
-  static bool attr_set[64] = {};                  // per device: opt in to > 48 KB of dynamic shared memory once
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t ce = cudaFuncSetAttribute(roi2_kernel<TAPS, HAS_MASK, FMT, LUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (ce != cudaSuccess) return ce;
-    attr_set[dev] = true;
-  }
-  roi2_kernel<TAPS, HAS_MASK, FMT, LUT><<<grid, block, smem, st>>>(rp);
-  return cudaGetLastError();
-}
-
 // streaming ROI kernels (roi_stream.cuh): persistent grid, CTAs per SM from the occupancy calculator
 template <int TAPS, bool HAS_MASK, int FMT, int MAXT, int MINB>
 cudaError_t roi3_launch(const Roi3Params& rp, int num_sms, int ctas_per_sm, int block, size_t smem, cudaStream_t st) {
@@ -882,45 +861,6 @@ int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W
         default: ce = cudaErrorInvalidValue; break;
       }
 #undef ROI3_CASE
-      if (ce != cudaSuccess) return fail(FLOPE_ECUDA, std::string("ROI kernel launch: ") + cudaGetErrorString(ce));
-      ++e->launches;
-      return FLOPE_OK;
-    }
-  }
-  // ---- staged kernels: frame rows whose alignment modulo 4 does not depend on the row, output side up to 512 ----
-  if (e->roi_staged && W % 4 == 0 && S <= 512 && n_frames >= 1 && (out_fmt != FLOPE_OUT_ENGINE || rp.g.plane * 16 < (1LL << 32))) {
-    rp.frames_end = d_frames + (long long)(n_frames - 1) * frame_stride + (long long)H * W * 3;
-    rp.masks_end = has_mask ? d_masks + (long long)n_frames * rp.mask_stride : nullptr;
-    int block;
-    if (lanczos) {
-      rp.cols_cta = S <= 256 ? S : (S / 2 + 1) / 2 * 2;
-      rp.n_sub = 1;
-      block = (rp.cols_cta + 31) / 32 * 32;
-      rp.rows_per_strip = std::min(kRoiMaxStripRows, e->roi_strip8);
-    } else {
-      rp.cols_cta = S <= 256 ? S : (S / 2 + 1) / 2 * 2;
-      const int pairs = rp.cols_cta / 2;
-      rp.n_sub = std::max(1, std::min(e->roi_sub, 256 / pairs));
-      block = (pairs * rp.n_sub + 31) / 32 * 32;
-      rp.rows_per_strip = std::min(kRoiMaxStripRows, e->roi_strip);
-    }
-    // the staging area must hold a few rows of the widest box the frame admits (a box may be the whole frame)
-    const int widest = std::max(H, W);
-    const int min_rows = lanczos ? 12 : 4;
-    rp.data_bytes = std::max(e->roi_data_kb * 1024, min_rows * (4 * widest + 160));
-    const Roi2Layout L = roi2_layout(lanczos ? 8 : 2, rp.cols_cta, rp.rows_per_strip, rp.data_bytes);
-    if (L.total <= kMaxSmem) {
-      dim3 grid((S + rp.cols_cta - 1) / rp.cols_cta, (S + rp.rows_per_strip - 1) / rp.rows_per_strip, n);
-      cudaError_t ce;
-      const int key = (lanczos ? 4 : 0) | (has_mask ? 2 : 0) | (out_fmt == FLOPE_OUT_ENGINE ? 1 : 0);
-      const bool lut = e->roi_lut != 0;
-#define ROI2_CASE(K, T, M, F) case K: ce = lut ? roi2_launch<T, M, F, true>(rp, grid, block, L.total, st) : roi2_launch<T, M, F, false>(rp, grid, block, L.total, st); break;
-      switch (key) {
-        ROI2_CASE(0, 2, false, 0) ROI2_CASE(1, 2, false, 1) ROI2_CASE(2, 2, true, 0) ROI2_CASE(3, 2, true, 1)
-        ROI2_CASE(4, 8, false, 0) ROI2_CASE(5, 8, false, 1) ROI2_CASE(6, 8, true, 0)
-        default: ce = lut ? roi2_launch<8, true, 1, true>(rp, grid, block, L.total, st) : roi2_launch<8, true, 1, false>(rp, grid, block, L.total, st); break;
-      }
-#undef ROI2_CASE
       if (ce != cudaSuccess) return fail(FLOPE_ECUDA, std::string("ROI kernel launch: ") + cudaGetErrorString(ce));
       ++e->launches;
       return FLOPE_OK;
@@ -1344,12 +1284,6 @@ int flope_debug_timeline(flope_engine* e, unsigned long long* out, int max_launc
 int flope_debug_set(flope_engine* e, const char* key, int value) {
   if (!e || !key) return fail(FLOPE_EINVAL, "NULL argument");
   if (!std::strcmp(key, "use_graph")) { e->use_graph = value != 0; return FLOPE_OK; }
-  if (!std::strcmp(key, "roi_strip") || !std::strcmp(key, "roi_strip8")) {
-    if (value < 2 || value > kRoiMaxStripRows || (value & 1)) return fail(FLOPE_EINVAL, "roi_strip must be even and in [2,128]");
-    (key[9] ? e->roi_strip8 : e->roi_strip) = value;
-    return FLOPE_OK;
-  }
-  if (!std::strcmp(key, "roi_staged")) { e->roi_staged = value != 0; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_stream")) { e->roi_stream = value; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_item_rows") || !std::strcmp(key, "roi_item_rows8")) {
     if (value < 1 || value > kR3MaxItemRows) return fail(FLOPE_EINVAL, "roi_item_rows must be in [1,128]");
@@ -1368,17 +1302,6 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
   }
   if (!std::strcmp(key, "roi_dynamic")) { e->roi_dynamic = value; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_ctas_per_sm")) { e->roi_ctas_per_sm = value; return FLOPE_OK; }
-  if (!std::strcmp(key, "roi_lut")) { e->roi_lut = value != 0; return FLOPE_OK; }
-  if (!std::strcmp(key, "roi_sub")) {
-    if (value < 1 || value > 8) return fail(FLOPE_EINVAL, "roi_sub must be in [1,8]");
-    e->roi_sub = value;
-    return FLOPE_OK;
-  }
-  if (!std::strcmp(key, "roi_data_kb")) {
-    if (value < 8 || value > 200) return fail(FLOPE_EINVAL, "roi_data_kb must be in [8,200]");
-    e->roi_data_kb = value;
-    return FLOPE_OK;
-  }
   if (!std::strcmp(key, "chain_coop")) { e->chain_coop = value != 0; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "timeline")) {
     drop_graphs(e);

@@ -91,25 +91,42 @@ def _b5(boxes, frame=0):
     return torch.from_numpy(np.concatenate([np.full((len(boxes), 1), frame, np.int32), np.asarray(boxes, np.int32)], 1)).cuda()
 
 
+# (stream, item rows, stage KB, ring stages, CTAs per SM, dynamic claiming): the streaming kernels under several launch
+# geometries - tiny stages (one or two rows per stage), short and tall items, a single CTA per SM - and the generic kernel
+_ROI_MODES = [(1, 0, 0, 0, 0, 1), (1, 7, 1, 2, 1, 0), (1, 16, 4, 4, 0, 1), (1, 128, 16, 3, 2, 1), (0, 0, 0, 0, 0, 1)]
+
+
+def _set_roi_mode(e, mode, lanczos):
+    stream, rows, kb, stages, per_sm, dyn = mode
+    e.debug_set("roi_stream", stream)
+    if rows:
+        e.debug_set("roi_item_rows8" if lanczos else "roi_item_rows", rows)
+        e.debug_set("roi_stage_kb", kb); e.debug_set("roi_stages", stages)
+    e.debug_set("roi_ctas_per_sm", per_sm); e.debug_set("roi_dynamic", dyn)
+
+
 @pytest.mark.parametrize("interp,size", [(R.LANCZOS4, 512), (R.BILINEAR, 224), (R.LANCZOS4, 224), (R.BILINEAR, 512)])
-def test_staged_kernels_match_generic_and_arithmetic_modes(cuda_lib, interp, size):
-    """The staged kernels (TMA-staged rows, DP2A taps), their table-free normalise variant and the generic
-    one-thread-per-column kernel are three implementations of the same integer arithmetic: bitwise equal."""
+def test_streaming_kernels_match_generic_under_every_geometry(cuda_lib, interp, size):
+    """The streaming kernels (TMA row ring, DP2A taps, FMA-pipe vertical pass) under different item / stage / grid
+    geometries and the generic one-thread-per-column kernel implement the same integer arithmetic: bitwise equal.
+    Repeated launches also exercise the self-resetting work counter."""
     rng = np.random.default_rng(21)
     frame, mask = _frame(rng)
     fr, mk, b5 = torch.from_numpy(frame).cuda()[None], torch.from_numpy(mask).cuda()[None], _b5(_boxes())
     e = cuda_lib.Engine(0, max_batch=16, crop_hw=size)
     outs = []
-    for staged, lut in ((1, 1), (1, 0), (0, 1)):
-        e.debug_set("roi_staged", staged); e.debug_set("roi_lut", lut)
-        outs.append(e.roi_crop(fr, mk, b5, size, interp).clone())
+    for mode in _ROI_MODES:
+        _set_roi_mode(e, mode, interp == R.LANCZOS4)
+        for m in (mk, None):
+            outs.append((m is None, e.roi_crop(fr, m, b5, size, interp).clone()))
     torch.cuda.synchronize()
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    for nomask, o in outs[2:]:
+        assert torch.equal(o, outs[1 if nomask else 0][1])
     e.close()
 
 
-def test_engine_format_staged_equals_generic(cuda_lib):
-    """bf16 stem-input crops of the staged kernels (both normalise variants) vs the generic kernel: identical PoseNet outputs."""
+def test_engine_format_streaming_equals_generic(cuda_lib):
+    """bf16 stem-input crops of the streaming kernels vs the generic kernel: identical PoseNet outputs."""
     from oracle import posenet as onet
     net = onet.build(0)
     e = cuda_lib.Engine(0, max_batch=16, crop_hw=224)
@@ -119,17 +136,18 @@ def test_engine_format_staged_equals_generic(cuda_lib):
     fr, mk, b5 = torch.from_numpy(frame).cuda()[None], torch.from_numpy(mask).cuda()[None], _b5(_boxes())
     for interp in (R.BILINEAR, R.LANCZOS4):
         outs = []
-        for staged, lut in ((1, 1), (1, 0), (0, 1)):
-            e.debug_set("roi_staged", staged); e.debug_set("roi_lut", lut)
+        for mode in _ROI_MODES:
+            _set_roi_mode(e, mode, interp == R.LANCZOS4)
             e.roi_crop(fr, mk, b5, 224, interp, out_fmt=cuda_lib.OUT_ENGINE)
             outs.append(e.posenet_forward(None, n=len(b5)).clone())
         torch.cuda.synchronize()
-        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), interp
+        for o in outs[1:]:
+            assert torch.equal(outs[0], o), interp
     e.close()
 
 
 @pytest.mark.parametrize("interp", [R.BILINEAR, R.LANCZOS4])
-def test_roi_frame_width_not_multiple_of_4_takes_generic_path(cuda_lib, eng, interp):
+def test_roi_frame_width_not_multiple_of_16_takes_generic_path(cuda_lib, eng, interp):
     rng = np.random.default_rng(23)
     frame, mask = _frame(rng, H=241, W=322)
     boxes = np.array([[0, 0, 241, 241], [81, 0, 322, 241], [13, 17, 150, 154], [300, 200, 322, 222]], np.int32)

@@ -54,19 +54,8 @@ for rows, kb, stages, per_sm, dyn in scfgs:
         report(f"stream rows={rows} kb={kb} stages={stages} per_sm={per_sm} dyn={dyn} bilinear->224 bf16 engine mask={int(mask_on)}", ms,
                by_m if mask_on else by_n, n)
 eng.debug_set("roi_stream", 0)
-eng.debug_set("roi_staged", 0)
 ms = timeit(lambda: eng.roi_crop(fr, mk, bx, 224, _lib.INTERP_LINEAR, out_fmt=_lib.OUT_ENGINE))
 report("generic  bilinear->224 bf16 engine mask=1", ms, by_m, n)
-eng.debug_set("roi_staged", 1)
-cfgs = [(32, 2, 36, 1)] if quick else [(32, 2, 36, 1), (32, 2, 36, 0), (16, 2, 24, 1), (64, 2, 48, 1), (32, 1, 36, 1),
-                                       (16, 1, 24, 1), (64, 2, 48, 0), (28, 2, 36, 1), (56, 2, 48, 1)]
-for strip, sub, kb, lut in cfgs:
-    eng.debug_set("roi_strip", strip); eng.debug_set("roi_sub", sub); eng.debug_set("roi_data_kb", kb); eng.debug_set("roi_lut", lut)
-    for mask_on in (True, False):
-        m = mk if mask_on else None
-        ms = timeit(lambda: eng.roi_crop(fr, m, bx, 224, _lib.INTERP_LINEAR, out_fmt=_lib.OUT_ENGINE))
-        report(f"staged strip={strip} sub={sub} kb={kb} lut={lut} bilinear->224 bf16 engine mask={int(mask_on)}", ms,
-               by_m if mask_on else by_n, n)
 eng.close()
 
 nb = min(n, 256)
@@ -84,16 +73,7 @@ for rows, kb, stages in ([(128, 10, 3)] if quick else [(128, 10, 3), (64, 10, 3)
                byts if mask_on else float((3 * s ** 2 + 3145728 + 20).sum()), nb)
 eng.debug_set("roi_stage_kb", 10); eng.debug_set("roi_stages", 3)
 eng.debug_set("roi_stream", 0)
-eng.debug_set("roi_staged", 0)
 for interp, name in ((_lib.INTERP_LANCZOS4, "lanczos4"), (_lib.INTERP_LINEAR, "bilinear")):
     ms = timeit(lambda: eng.roi_crop(fr, mk, bx[:nb], 512, interp, out=out), reps=5)
     report(f"generic  {name}->512 f32 NCHW mask=1", ms, byts, nb)
-eng.debug_set("roi_staged", 1)
-for strip8, kb, lut in ([(128, 36, 1)] if quick else [(128, 36, 1), (128, 36, 0), (64, 36, 1), (128, 64, 1), (64, 24, 0)]):
-    eng.debug_set("roi_strip8", strip8); eng.debug_set("roi_data_kb", kb); eng.debug_set("roi_lut", lut)
-    ms = timeit(lambda: eng.roi_crop(fr, mk, bx[:nb], 512, _lib.INTERP_LANCZOS4, out=out), reps=5)
-    report(f"staged strip8={strip8} kb={kb} lut={lut} lanczos4->512 f32 NCHW mask=1", ms, byts, nb)
-eng.debug_set("roi_strip", 32); eng.debug_set("roi_data_kb", 36); eng.debug_set("roi_lut", 1)
-ms = timeit(lambda: eng.roi_crop(fr, mk, bx[:nb], 512, _lib.INTERP_LINEAR, out=out), reps=5)
-report("staged bilinear->512 f32 NCHW mask=1", ms, byts, nb)
 eng.close()
