@@ -110,3 +110,48 @@ def test_product_random_init_equals_oracle_init():
     assert list(sd.keys()) == list(ref.keys())
     for k in ref:
         assert torch.equal(sd[k], ref[k]), k
+
+
+def _davenport_q_method(m):
+    """Nearest rotation to M (maximises tr(R^T M)) WITHOUT an SVD: Davenport's q-method - the optimal unit quaternion is
+    the eigenvector of the symmetric 4x4 matrix K(M) with the largest eigenvalue (Wahba's problem with attitude profile M).
+    An independent second derivation of what oracle.rotation.special_procrustes (R = U diag(1,1,det) V^T) computes."""
+    m = np.asarray(m, np.float64)
+    out = np.empty_like(m)
+    for i, B in enumerate(m):
+        S, sig = B + B.T, np.trace(B)
+        z = np.array([B[1, 2] - B[2, 1], B[2, 0] - B[0, 2], B[0, 1] - B[1, 0]])
+        K = np.zeros((4, 4))
+        K[:3, :3] = S - sig * np.eye(3)
+        K[:3, 3] = K[3, :3] = z
+        K[3, 3] = sig
+        w, v = np.linalg.eigh(K)
+        q = v[:, -1]
+        qv, q4 = q[:3], q[3]
+        qx = np.array([[0, -qv[2], qv[1]], [qv[2], 0, -qv[0]], [-qv[1], qv[0], 0]])
+        out[i] = (q4 * q4 - qv @ qv) * np.eye(3) + 2 * np.outer(qv, qv) - 2 * q4 * qx
+    return out
+
+
+def test_special_procrustes_agrees_with_an_svd_free_formulation():
+    """roma.special_procrustes is absent (parity unpinned, oracle/rotation.py): at least pin the restatement against a
+    second, independent formulation of 'the rotation nearest to M' - on random matrices, on small 9-vectors like a
+    random-init head produces, on reflections (det < 0) and on rank-2 matrices, where the answer is still unique."""
+    rng = np.random.default_rng(12)
+    m = rng.standard_normal((600, 3, 3))
+    m[:200] *= 0.05
+    m[200:300] = m[200:300] @ np.diag([1.0, 1.0, -1.0])                       # plenty of det < 0
+    u, s, vt = np.linalg.svd(m[300:400])
+    s[:, 2] = 0.0                                                             # rank 2
+    m[300:400] = (u * s[:, None, :]) @ vt
+    m[400] = np.diag([1.0, 1.0, -1.0])                                        # pure reflection: the nearest rotation is not unique
+    want = orot.special_procrustes(torch.from_numpy(m)).numpy()
+    got = _davenport_q_method(m)
+    sv = np.linalg.svd(m, compute_uv=False)
+    gap = sv[:, 1] + np.sign(np.linalg.det(m)) * sv[:, 2]                     # uniqueness margin of the maximiser
+    ok = gap / sv[:, 0] > 1e-6
+    assert ok.sum() >= 590
+    assert orot.geodesic_deg(got[ok], want[ok]).max() < 1e-5
+    obj = lambda R: np.einsum('nij,nij->n', R, m)                             # both maximise tr(R^T M), unique or not
+    assert np.abs(obj(got) - obj(want)).max() < 1e-9
+    assert np.abs(np.linalg.det(want) - 1).max() < 1e-9
