@@ -120,6 +120,8 @@ struct ConvChain {
   int n_m_tiles;               // position tiles per layer
   uint32_t* flags;             // [n_layers][n_m_tiles] completion counters, zeroed before the launch (nullptr: single layer)
   uint32_t expected;           // counter value of a finished position tile
+  uint32_t* fail;              // device word set when a dependency wait timed out (see wait_tile_flag); zeroed with the flags
+  uint32_t* host_err;          // the same, in mapped host memory, sticky until the host reads it
   // Dynamic work claiming (optional, chains only): items are handed out in index order by an atomic counter instead
   // of round-robin by block index.  Every claimed item then belongs to a CTA that is RESIDENT, and all the items it
   // waits on have lower indices, i.e. were claimed earlier by resident CTAs - so the tile-flag waits cannot deadlock
@@ -142,13 +144,29 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Bounded spin until the counter reaches `expected` (a dependency bug must trap, never hang the box).
-__device__ __forceinline__ void wait_tile_flag(const uint32_t* flag, uint32_t expected) {
+// Wait until the counter reaches `expected`.  The wait is bounded in TIME (a tile whose producer CTA never became
+// resident - another context's kernels hold the SMs - must not hang the box): after kTileWaitNs the CTA records the
+// failure in `fail` (device word, zeroed with the flags; every other wait of the launch then gives up at once) and in
+// `host_err` (mapped host word: the next API call on any engine of the process reports FLOPE_ECUDA), and carries on
+// with whatever is in memory, so that the launch terminates instead of trapping the context.
+constexpr unsigned long long kTileWaitNs = 5000000000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void wait_tile_flag(const uint32_t* flag, uint32_t expected, uint32_t* fail, uint32_t* host_err) {
+  if (ld_acquire_gpu(flag) >= expected) return;
+  const unsigned long long t0 = global_timer_ns();
   uint32_t spins = 0;
   while (ld_acquire_gpu(flag) < expected) {
-    if (++spins > (1u << 22)) {
-      printf("flope: tile-flag timeout block=%d thread=%d\n", blockIdx.x, threadIdx.x);
-      __trap();
+    if ((++spins & 1023u) == 0) {
+      if (fail && ld_acquire_gpu(fail)) return;
+      if (global_timer_ns() - t0 > kTileWaitNs) {
+        if (fail) atomicExch(fail, 1u);
+        if (host_err) { atomicExch_system(host_err, 1u); __threadfence_system(); }
+        return;
+      }
     }
   }
 }
@@ -324,9 +342,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         // the producing layer's tiles under this tile's halo must be complete (and visible to the TMA unit)
         const int m = w / p.n_n_tiles;
         const uint32_t* fl = ch.flags + (size_t)(l - 1) * ch.n_m_tiles;
-        if (m > 0) wait_tile_flag(fl + m - 1, ch.expected);
-        wait_tile_flag(fl + m, ch.expected);
-        if (m + 1 < ch.n_m_tiles) wait_tile_flag(fl + m + 1, ch.expected);
+        if (m > 0) wait_tile_flag(fl + m - 1, ch.expected, ch.fail, ch.host_err);
+        wait_tile_flag(fl + m, ch.expected, ch.fail, ch.host_err);
+        if (m + 1 < ch.n_m_tiles) wait_tile_flag(fl + m + 1, ch.expected, ch.fail, ch.host_err);
         asm volatile("fence.proxy.async;" ::: "memory");
       }
       for (int tt = 0; tt < tiles_per_work; ++tt) {
@@ -592,7 +610,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const uint32_t acc = tmem_base + stage * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
         bool waited = false;
         if (q.res_layer >= 0) {                 // residual written earlier in this launch: its tile must be published
-          wait_tile_flag(ch.flags + (size_t)q.res_layer * ch.n_m_tiles + w / p.n_n_tiles, ch.expected);
+          wait_tile_flag(ch.flags + (size_t)q.res_layer * ch.n_m_tiles + w / p.n_n_tiles, ch.expected, ch.fail, ch.host_err);
           __syncwarp();
         }
 #pragma unroll 1

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -164,6 +165,56 @@ bool conv_launch(int n_tile, int mt, bool pair, int taps, const ConvChain& c, di
 #undef X
   return false;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Process-wide plumbing for the launches that need their whole grid resident (stage chains, trunk launch)
+// ---------------------------------------------------------------------------------------------
+// Sticky error word in mapped host memory: a tile-dependency wait that timed out on the device sets it (conv_igemm.cuh:
+// wait_tile_flag), the next API call reports FLOPE_ECUDA.  device = true returns the device-side alias.
+uint32_t* host_err_word(bool device) {
+  static uint32_t* h = nullptr;
+  static uint32_t* d = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* hp = nullptr;
+    if (cudaHostAlloc(&hp, sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return; }
+    *static_cast<uint32_t*>(hp) = 0u;
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(hp); return; }
+    h = static_cast<uint32_t*>(hp); d = static_cast<uint32_t*>(dp);
+  });
+  return device ? d : h;
+}
+bool take_device_timeout() {
+  volatile uint32_t* h = host_err_word(false);
+  if (h && *h) { *h = 0u; return true; }
+  return false;
+}
+
+// The chain / trunk kernels deal tiles statically and spin on each other's completion flags: every CTA of such a launch
+// must be resident, which holds as long as only ONE of them runs on the device at a time.  Engines are independent
+// objects (the header allows calls on different engines from different threads and streams), so the library enforces
+// it itself: a forward that contains such launches waits for the previous one on the same device (an event chain;
+// the host mutex keeps wait -> launch -> record atomic across threads).  On one stream the wait is already satisfied
+// and costs a microsecond of host time; per-layer launches (EnginePool's overlapping engines) never take the gate.
+struct ResidencyGate {
+  struct PerDevice { std::mutex mu; cudaEvent_t ev = nullptr; bool recorded = false; };
+  static PerDevice& of(int dev) { static PerDevice g[64]; return g[dev & 63]; }
+  PerDevice* g = nullptr;
+  cudaStream_t st = nullptr;
+  ResidencyGate(bool needed, int dev, cudaStream_t stream) {
+    if (!needed) return;
+    g = &of(dev); st = stream;
+    g->mu.lock();
+    if (!g->ev && cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); g->ev = nullptr; }
+    if (g->ev && g->recorded) cudaStreamWaitEvent(st, g->ev, 0);
+  }
+  ~ResidencyGate() {
+    if (!g) return;
+    if (g->ev && cudaEventRecord(g->ev, st) == cudaSuccess) g->recorded = true;
+    g->mu.unlock();
+  }
+};
 
 }  // namespace
 
@@ -597,6 +648,8 @@ int build_chain(flope_engine* e, ConvLayer* const* Ls, int count, int n, uint32_
   c.claim_static = e->chain_dynamic == 2;
   c.claims = (count > 1 && e->chain_dynamic) ? flags + kChainHeader / 2 : nullptr;
   c.expected = (uint32_t)(c.L[0].n_n_tiles * (L0.pair ? 2 : 1));
+  c.fail = e->d_flags ? e->d_flags + 1 : nullptr;      // one word for every chain of the engine (header of the first chain)
+  c.host_err = host_err_word(true);
   return FLOPE_OK;
 }
 
@@ -750,6 +803,10 @@ void drop_graphs(flope_engine* e) {
 // The ~23 backbone launches of one batch size are captured once into a CUDA graph (engine-internal
 // buffers only, so every kernel argument is fixed for a given n) and replayed with one launch.
 int run_backbone(flope_engine* e, int n, cudaStream_t st) {
+  if (take_device_timeout())
+    return fail(FLOPE_ECUDA, "a tile-dependency wait timed out in an earlier launch (its CTAs were not all resident: the SMs were held "
+                             "by other work for seconds); the results of that call are invalid");
+  ResidencyGate gate(e->use_chain && !e->chain_coop && !e->chain_dynamic, e->device, st);
   if (!e->use_graph || e->profile) return run_backbone_launches(e, n, st);
   for (auto& g : e->graphs)
     if (g.n == n) {
@@ -910,15 +967,19 @@ int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) return fail(FLOPE_ECUDA, "flope_b200 kernels are built for sm_100a (B200) only");
+  // the library carries sm_100a code only, and arch-specific targets do not run on other 10.x parts
+  if (prop.major != 10 || prop.minor != 0) return fail(FLOPE_ECUDA, "flope_b200 kernels are built for sm_100a (B200, compute capability 10.0) only");
+  if (prop.multiProcessorCount > 148) return fail(FLOPE_ECUDA, "more than 148 SMs: the claim slots and stamp buffers are sized for B200");
   CUDA_TRY(conv_set_all_attrs());
   flope_engine* e = new flope_engine();
   e->device = device; e->max_batch = max_batch; e->S = crop_hw;
   e->num_sms = prop.multiProcessorCount;
   int rc = build_network(e);
-  if (rc) { delete e; return rc; }
+  // from here on every early return (CUDA_TRY included) releases what has been allocated so far
+  std::unique_ptr<flope_engine, void (*)(flope_engine*)> guard(e, flope_engine_destroy);
+  if (rc) return rc;
   for (ActBuf& b : e->bufs) {
-    if (cudaMalloc(&b.d, b.bytes()) != cudaSuccess) { flope_engine_destroy(e); return fail(FLOPE_ENOMEM, "activation buffer allocation failed"); }
+    if (cudaMalloc(&b.d, b.bytes()) != cudaSuccess) { cudaGetLastError(); return fail(FLOPE_ENOMEM, "activation buffer allocation failed"); }
     CUDA_TRY(cudaMemset(b.d, 0, b.bytes()));
   }
   CUDA_TRY(cudaMalloc(&e->d_feat, (size_t)(e->max_batch + kMaxTM) * e->feat_dim * sizeof(float)));
@@ -928,8 +989,8 @@ int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_
   CUDA_TRY(cudaMemset(e->d_roi_sched, 0, 2 * sizeof(unsigned int)));
   CUDA_TRY(cudaMalloc(&e->d_r9, (size_t)e->max_batch * 9 * sizeof(float)));
   for (ConvLayer& L : e->layers)
-    if ((rc = plan_conv(e, L))) { flope_engine_destroy(e); return rc; }
-  if (e->can_fuse_pool && (rc = plan_conv(e, e->stem_pool))) { flope_engine_destroy(e); return rc; }
+    if ((rc = plan_conv(e, L))) return rc;
+  if (e->can_fuse_pool && (rc = plan_conv(e, e->stem_pool))) return rc;
   {
     // completion counters of the chains: kMaxChain layers x position tiles at max_batch (the smallest tile is 128 positions)
     size_t per = 0;
@@ -941,7 +1002,7 @@ int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_
     if (per) CUDA_TRY(cudaMalloc(&e->d_flags, e->chains.size() * per * sizeof(uint32_t)));
   }
   CUDA_TRY(cudaDeviceSynchronize());
-  *out = e;
+  *out = guard.release();
   return FLOPE_OK;
 }
 
@@ -1192,7 +1253,10 @@ int flope_depth_values(int device, const void* d_depth, int depth_dtype, float d
     // (sum, count) accumulators of the row-stripe CTAs: n x 16 bytes from the stream-ordered pool
     unsigned long long* acc = nullptr;
     CUDA_TRY(cudaMallocAsync(&acc, (size_t)n * 2 * sizeof(unsigned long long), st));
-    CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)n * 2 * sizeof(unsigned long long), st));
+    if (cudaError_t ce = cudaMemsetAsync(acc, 0, (size_t)n * 2 * sizeof(unsigned long long), st)) {
+      cudaFreeAsync(acc, st);
+      return fail(FLOPE_ECUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(ce));
+    }
     box_depth_kernel<<<dim3(n, kBoxSplit), 256, 0, st>>>(dp, d_boxes, acc);
     box_depth_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(acc, n, d_val, d_count);
     CUDA_TRY(cudaFreeAsync(acc, st));
@@ -1279,6 +1343,17 @@ int flope_debug_timeline(flope_engine* e, unsigned long long* out, int max_launc
   const int n = std::min(std::min(max_launches, e->stamp_launch), kStampLaunches);
   CUDA_TRY(cudaMemcpy(out, e->d_stamps, (size_t)n * 148 * kStampWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return n;
+}
+
+int flope_engine_set_schedule(flope_engine* e, int schedule) {
+  if (!e) return fail(FLOPE_EINVAL, "NULL argument");
+  if (schedule < FLOPE_SCHED_PERSISTENT || schedule > FLOPE_SCHED_COOPERATIVE) return fail(FLOPE_EINVAL, "unknown schedule");
+  e->use_chain = schedule != FLOPE_SCHED_PER_LAYER;
+  e->use_trunk = schedule == FLOPE_SCHED_PERSISTENT;
+  e->chain_dynamic = schedule == FLOPE_SCHED_DYNAMIC ? 1 : 0;
+  e->chain_coop = schedule == FLOPE_SCHED_COOPERATIVE;
+  drop_graphs(e);
+  return FLOPE_OK;
 }
 
 int flope_debug_set(flope_engine* e, const char* key, int value) {

@@ -24,8 +24,10 @@
 //     (folded into conv2 as extra K) reads positions its own conv1 neighbours already waited for;
 //   * the epilogue warps re-stage the stage's folded-BN biases between two named barriers of their own; each stage's
 //     rings start right behind its own bias block.
-// Static dealing needs every CTA resident (grid <= SM count, one engine per device at a time) - the same condition as
-// the per-stage chains; engines that share a device keep per-layer launches (pipeline.EnginePool).
+// Static dealing needs every CTA resident (grid <= SM count, one such launch on the device at a time) - the same
+// condition as the per-stage chains.  engine.cu enforces it: forwards that contain these launches pass a per-device
+// gate (an event chain under a host mutex), so two engines on two streams run their backbones one after the other;
+// engines meant to overlap (pipeline.EnginePool) use per-layer launches, which wait for nothing.
 #pragma once
 #include "conv_igemm.cuh"
 
@@ -106,9 +108,9 @@ struct TrunkStage {
       const int tile_start = m * TILE_POS + (int)c.rank * TM;
       if (l > 0) {
         const uint32_t* fl = ch.flags + (size_t)(l - 1) * ch.n_m_tiles;
-        if (m > 0) wait_tile_flag(fl + m - 1, ch.expected);
-        wait_tile_flag(fl + m, ch.expected);
-        if (m + 1 < ch.n_m_tiles) wait_tile_flag(fl + m + 1, ch.expected);
+        if (m > 0) wait_tile_flag(fl + m - 1, ch.expected, ch.fail, ch.host_err);
+        wait_tile_flag(fl + m, ch.expected, ch.fail, ch.host_err);
+        if (m + 1 < ch.n_m_tiles) wait_tile_flag(fl + m + 1, ch.expected, ch.fail, ch.host_err);
         asm volatile("fence.proxy.async;" ::: "memory");
       } else if (prev != nullptr) {
         // stride-2 conv over the previous stage's output: half-res rows under this CTA's halo tile -> full-res rows
@@ -127,7 +129,7 @@ struct TrunkStage {
           int t_hi = hi / prev_tile_pos;
           t_hi = t_hi < prev->n_m_tiles ? t_hi : prev->n_m_tiles - 1;
           const uint32_t* fl = prev->flags + (size_t)(prev->n_layers - 1) * prev->n_m_tiles;
-          for (int t = t_lo; t <= t_hi; ++t) wait_tile_flag(fl + t, prev->expected);
+          for (int t = t_lo; t <= t_hi; ++t) wait_tile_flag(fl + t, prev->expected, ch.fail, ch.host_err);
           asm volatile("fence.proxy.async;" ::: "memory");
         }
       }
@@ -274,7 +276,7 @@ struct TrunkStage {
       const uint32_t acc = c.tmem_base + stage * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
       bool waited = false;
       if (q.res_layer >= 0) {
-        wait_tile_flag(ch.flags + (size_t)q.res_layer * ch.n_m_tiles + w / p.n_n_tiles, ch.expected);
+        wait_tile_flag(ch.flags + (size_t)q.res_layer * ch.n_m_tiles + w / p.n_n_tiles, ch.expected, ch.fail, ch.host_err);
         __syncwarp();
       }
 #pragma unroll 1

@@ -29,21 +29,16 @@ class EnginePool:
         self.serial_backbones = serial_backbones
         self._last_run = None
         if n_engines > 1 and not serial_backbones:
-            # Stage chains (one persistent launch per ResNet stage whose tiles wait for each other) need every CTA of a
-            # chain kernel to become resident.  Two chain kernels from two streams could each hold part of the SMs while
-            # waiting for their own unscheduled CTAs, so engines that run concurrently either launch one kernel per
-            # layer (default) or launch their chains cooperatively (gang-scheduled grids; 1 % faster than per-layer
-            # launches, but Nsight Compute cannot profile cooperative cluster launches: "LaunchFailed"), or let the
-            # chains claim their work items from an atomic counter (every claimed item then belongs to a resident CTA
-            # and only waits on lower items: deadlock-free under partial residency, profilable, but no faster than
+            # The default schedule (layer1..layer4 as one persistent launch whose tiles wait for each other) needs its
+            # whole grid resident; the library therefore runs such launches one at a time per device (engine.cu,
+            # ResidencyGate), which is safe but gives no backbone overlap.  Engines that should overlap pick a schedule
+            # that waits for nothing: one launch per layer (default here), cooperative stage chains (gang-scheduled; 1 %
+            # faster, but Nsight Compute cannot profile cooperative cluster launches) or stage chains that claim their
+            # work items from an atomic counter (deadlock-free under partial residency, profilable, no faster than
             # per-layer launches - 923 vs 911 vs 904 us/step for dynamic / per-layer / cooperative, two engines).
+            sched = _lib.SCHED_DYNAMIC if dynamic_chains else _lib.SCHED_COOPERATIVE if cooperative_chains else _lib.SCHED_PER_LAYER
             for e in self.engines:
-                if dynamic_chains:
-                    e.debug_set("chain_dynamic", 1)
-                elif cooperative_chains:
-                    e.debug_set("chain_coop", 1)
-                else:
-                    e.debug_set("chain", 0)
+                e.set_schedule(sched)
         if state_dict is not None:
             for e in self.engines:
                 e.load_state_dict(state_dict)

@@ -128,15 +128,25 @@ class _PredictorBase:
         (what scripts/test_posenet.py:144-161 writes) when nullify_yaw=False.
         """
         eng = self.posenet.engine
+        sq_bb = np.asarray(sq_bb)
+        if (sq_bb[:, 2] <= sq_bb[:, 0]).any() or (sq_bb[:, 3] <= sq_bb[:, 1]).any():
+            # the reference hands such a slice to cv2.resize, which raises (pose_predictor.py:145)
+            raise ValueError("empty box (xmax <= xmin or ymax <= ymin) after squarify")
         with torch.cuda.device(self.device):
-            frame = torch.from_numpy(np.ascontiguousarray(rgb)).to(self.device, non_blocking=True)[None]
-            if mask is None or torch.is_tensor(mask):
-                msk = mask
+            frame = torch.from_numpy(np.ascontiguousarray(rgb, dtype=np.uint8)).to(self.device, non_blocking=True)[None]
+            if mask is None:
+                msk = None
+            elif torch.is_tensor(mask):
+                msk = mask.to(self.device)
+                if msk.dtype == torch.bool:
+                    msk = msk.to(torch.uint8) * 255
+                elif msk.dtype != torch.uint8:
+                    msk = msk.to(torch.uint8)
+                msk = msk.reshape(1, *msk.shape[-2:]).contiguous()
             else:
-                msk = torch.from_numpy(np.ascontiguousarray(mask)).to(self.device)[None]
+                msk = torch.from_numpy(np.ascontiguousarray(mask, dtype=np.uint8)).to(self.device)[None]
             b5 = np.zeros((sq_bb.shape[0], 5), np.int32)
             b5[:, 1:] = sq_bb
-            b5 = torch.from_numpy(b5).to(self.device)
             _, R, Ry = eng.infer_frames(frame, msk, b5, self.interp, want_R=not nullify_yaw, want_yaw=nullify_yaw)
             return (Ry if nullify_yaw else R).cpu().numpy()
 

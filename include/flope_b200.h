@@ -12,12 +12,17 @@
  * is stream-ordered on the stream argument (a cudaStream_t passed as void*); there is no
  * hidden device synchronisation: the caller synchronises.  The caller owns every input and
  * output buffer; the engine owns weights and workspace sized by max_batch.  One engine per
- * (device, stream): calls on different engines may run concurrently, calls on one engine
- * may not.  Engines whose kernels can be in flight on the SAME device at the same time must
- * launch their stage chains cooperatively (flope_debug_set(e, "chain_coop", 1)), let them claim
- * their work dynamically ("chain_dynamic", 1) or switch them off ("chain", 0): a chain kernel's tiles wait for each other and rely on all of its CTAs becoming
- * resident, which two such kernels competing for the SMs do not guarantee unless the launch is
- * gang-scheduled (flope_b200.pipeline.EnginePool switches the chains of its engines off by default).
+ * (device, stream): calls on different engines may run concurrently (from different threads
+ * and streams), calls on one engine may not.  Concurrency on one device is safe by
+ * construction: the default schedule runs layer1..layer4 as persistent launches whose CTAs
+ * wait for each other's tiles and therefore need the whole grid resident, so the library
+ * passes every forward that contains such a launch through a per-device gate (an event
+ * chain under a host mutex) - two engines on two streams run their backbones one after the
+ * other and overlap everything else.  Engines that are meant to overlap their backbones
+ * select a schedule that waits for nothing, flope_engine_set_schedule(e, FLOPE_SCHED_PER_LAYER).
+ * A dependency wait that still times out (the SMs held for seconds by another context's
+ * kernels) does not trap: the launch finishes, its results are invalid, and the next call on
+ * any engine of the process returns FLOPE_ECUDA once.
  */
 #ifndef FLOPE_B200_H
 #define FLOPE_B200_H
@@ -38,6 +43,11 @@ extern "C" {
 #define FLOPE_INTERP_LANCZOS4 1   /* cv2.INTER_LANCZOS4, bit-exact (the reference's mode)            */
 #define FLOPE_OUT_F32_NCHW 0      /* (B,3,S,S) float32, the tensor the reference builds              */
 #define FLOPE_OUT_ENGINE 1        /* write straight into the engine's bf16 stem input                */
+
+#define FLOPE_SCHED_PERSISTENT 0  /* default: one persistent launch for layer1..layer4, serialised per device        */
+#define FLOPE_SCHED_PER_LAYER 1   /* one launch per layer: nothing waits, engines on different streams overlap       */
+#define FLOPE_SCHED_DYNAMIC 2     /* stage chains that claim work from a counter: safe under partial residency       */
+#define FLOPE_SCHED_COOPERATIVE 3 /* stage chains launched cooperatively (gang-scheduled)                            */
 
 typedef struct flope_engine flope_engine;
 
@@ -176,6 +186,9 @@ int flope_debug_normalise_lut(float* d_out, void* stream);
  * "pair", "small_tiles" and "fc_small" change the packed-weight layout: call flope_engine_load_weights again afterwards.
  * Activation names for flope_debug_activation additionally include "x0" (the stem's space-to-depth input). */
 int flope_debug_set(flope_engine* e, const char* key, int value);
+/* How the backbone of this engine is launched (FLOPE_SCHED_*); see the concurrency paragraph at the top.  Product
+ * option (flope_b200.pipeline.EnginePool uses it), cheap: it only drops the engine's captured CUDA graphs. */
+int flope_engine_set_schedule(flope_engine* e, int schedule);
 /* After flope_debug_set(e, "timeline", 1): synchronise and copy the phase stamps of the conv_igemm launches of the
  * last forward, [launch][148 CTAs][8] uint64 (%globaltimer ns at kernel entry, prologue done, dependency wait done, first
  * operands landed, last MMA issued, first accumulator ready, last store issued, exit;

@@ -150,3 +150,51 @@ def test_gimbal_lock_follows_atan2_and_deviation_from_scipy_is_the_documented_on
                 assert np.abs(D[:, 0, 0] - 1).max() < 1e-4 and np.abs(D[:, 0, 1:]).max() < 1e-3 and np.abs(D[:, 1:, 0]).max() < 1e-3
     finally:
         e.close()
+
+
+def test_two_default_engines_on_two_streams_are_safe_and_bit_identical(cuda_lib, net):
+    """Two plain PoseResNet objects (default scheduling: layer1..layer4 as one persistent launch whose CTAs wait on each
+    other) driven from two streams, 200 interleaved steps: the library's per-device gate keeps the two launches from
+    sharing the SMs (no tile-flag time-out, no trap), and every result equals the single-engine result."""
+    from flope_b200.posenet import PoseResNet
+    ms = [PoseResNet(device="cuda:0", max_batch=64, crop_hw=224) for _ in range(2)]
+    for m in ms:
+        m.load_state_dict(net.state_dict())
+    xs = [synth.mixed_crops(64, 224, seed=40 + i).cuda() for i in range(2)]
+    refs = [ms[0](x).clone() for x in xs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    outs = []
+    for i in range(200):
+        k = i & 1
+        with torch.cuda.stream(streams[k]):
+            outs.append((i, ms[k](xs[(i >> 1) & 1]).clone()))
+    torch.cuda.synchronize()
+    for i, o in outs:
+        assert torch.equal(o, refs[(i >> 1) & 1]), i
+    # the engines still answer (no sticky device error)
+    assert torch.equal(ms[1](xs[0]), refs[0])
+
+
+def test_binding_rejects_what_the_kernels_would_misread(cuda_lib):
+    e = cuda_lib.Engine(0, max_batch=4, crop_hw=224)
+    try:
+        fr = torch.zeros((1, 64, 64, 3), dtype=torch.uint8, device="cuda")
+        ok = np.array([[0, 0, 0, 32, 32]], np.int32)
+        e.roi_crop(fr, None, ok, 224, ores.BILINEAR)
+        with pytest.raises(cuda_lib.FlopeError):
+            e.roi_crop(fr.float(), None, ok, 224, ores.BILINEAR)                                   # dtype
+        with pytest.raises(cuda_lib.FlopeError):
+            e.roi_crop(fr, torch.zeros((1, 32, 64), dtype=torch.uint8, device="cuda"), ok, 224, ores.BILINEAR)   # mask shape
+        with pytest.raises(cuda_lib.FlopeError):
+            e.roi_crop(fr, None, np.array([[1, 0, 0, 32, 32]], np.int32), 224, ores.BILINEAR)      # frame index
+        with pytest.raises(cuda_lib.FlopeError):
+            e.roi_crop(fr, None, np.array([[0, 5, 5, 5, 9]], np.int32), 224, ores.BILINEAR)        # empty box
+        with pytest.raises(cuda_lib.FlopeError):
+            e.roi_crop(fr.cpu(), None, ok, 224, ores.BILINEAR)                                     # host tensor
+        nc = torch.zeros((1, 64, 128, 3), dtype=torch.uint8, device="cuda")[:, :, ::2]            # non-contiguous: copied, not misread
+        assert torch.equal(e.roi_crop(nc, None, ok, 224, ores.BILINEAR), e.roi_crop(fr, None, ok, 224, ores.BILINEAR))
+        with pytest.raises(cuda_lib.FlopeError):
+            e.posenet_forward(torch.zeros((1, 3, 100, 100), device="cuda"))
+    finally:
+        e.close()
