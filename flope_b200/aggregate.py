@@ -51,61 +51,58 @@ def frame_measurements(det_path_or_arrays, depth, seg_mask, cam_pose_4x4, K, sca
 
 
 class Env3D:
+    """Re-identification of flowers across frames by nearest neighbour in the world frame, with running means.
+
+    A measurement closer than ``th`` (mm) to a known flower is merged into it - position by the weighted mean, orientation
+    by rot_average, weights = observation count so far vs 1 - and the flower's score grows by one; the rest start new
+    flowers with score 1.  get_final_data keeps the flowers seen more than ``score_th`` times.  When several measurements
+    of one frame pick the same flower the LAST one is merged and the score still grows by one (the reference's numpy
+    fancy assignment does exactly that), which is reproduced here by de-duplicating before one masked update.
+    ``all_new_trans`` / ``all_new_quat`` log, per frame that matched anything, the merged measurements in flower order
+    (zeros elsewhere) - the arrays scripts/align_measurements.py reads back."""
+
     def __init__(self, th=40, score_th=200):
-        """th: distance in mm below which two measurements are the same flower; score_th: observations needed."""
         self.th = th / 1000
         self.score_th = score_th
         self.num = 0
-        self.trans = None
-        self.quat = None
-        self.score = None
-        self.all_new_trans = []
-        self.all_new_quat = []
+        self.trans = self.quat = self.score = None
+        self.all_new_trans, self.all_new_quat = [], []
+
+    def _append(self, tvec, qvec):
+        self.trans = np.vstack((self.trans, tvec))
+        self.quat = np.vstack((self.quat, qvec))
+        self.score = np.concatenate((self.score, np.ones(tvec.shape[0])))
 
     def add_measurement(self, tvec, qvec):
-        """tvec (N,3), qvec (N,4): match to the known flowers, average matched ones, append the rest."""
+        """tvec (N,3) world-frame positions, qvec (N,4) xyzw orientations of one frame."""
         from scipy.spatial.distance import cdist
         if self.trans is None:
-            self.trans = tvec
-            self.quat = qvec
-            self.score = np.ones(tvec.shape[0])
+            self.trans, self.quat, self.score = tvec, qvec, np.ones(tvec.shape[0])
             self.all_new_trans.append(tvec)
             self.all_new_quat.append(qvec)
             return
-        distance_matrix = cdist(tvec, self.trans, metric='euclidean')
-        min_idx = np.argmin(distance_matrix, axis=1)
-        min_vals = np.min(distance_matrix, axis=1)
-        good_match = min_vals < self.th
-        min_idx_good = min_idx[good_match]
-        tvec_good = tvec[good_match]
-        qvec_good = qvec[good_match]
-        state_score = self.score[min_idx_good]
-        meas_score = np.ones(state_score.shape[0])
-        normalizer = state_score + meas_score
-        state_weight = state_score / normalizer
-        meas_weight = meas_score / normalizer
-        if min_idx_good.shape[0] == 0:
-            self.trans = np.vstack((self.trans, tvec))
-            self.quat = np.vstack((self.quat, qvec))
-            self.score = np.concatenate((self.score, np.ones(tvec.shape[0])))
-        else:
-            self.trans[min_idx_good] = self.trans[min_idx_good] * state_weight.reshape(-1, 1) + tvec_good * meas_weight.reshape(-1, 1)
-            self.quat[min_idx_good] = rot_average(self.quat[min_idx_good], qvec_good, state_weight, meas_weight)
-            new_trans = np.zeros_like(self.trans)
-            new_trans[min_idx_good] = tvec_good
-            self.all_new_trans.append(new_trans)
-            new_quat = np.zeros_like(self.quat)
-            new_quat[min_idx_good] = qvec_good
-            self.all_new_quat.append(new_quat)
-            self.score[min_idx_good] += 1
-            unmatched = np.logical_not(good_match)
-            self.trans = np.vstack((self.trans, tvec[unmatched]))
-            self.quat = np.vstack((self.quat, qvec[unmatched]))
-            self.score = np.concatenate((self.score, np.ones(int(unmatched.sum()))))
+        dist = cdist(tvec, self.trans, metric='euclidean')
+        nearest = dist.argmin(axis=1)
+        known = dist[np.arange(tvec.shape[0]), nearest] < self.th
+        if known.any():
+            # one measurement per flower: the last claimant
+            rows = np.flatnonzero(known)
+            flowers, first_from_end = np.unique(nearest[rows][::-1], return_index=True)
+            rows = rows[::-1][first_from_end]
+            seen = self.score[flowers]
+            w_old, w_new = seen / (seen + 1.0), 1.0 / (seen + 1.0)
+            self.trans[flowers] = self.trans[flowers] * w_old[:, None] + tvec[rows] * w_new[:, None]
+            self.quat[flowers] = rot_average(self.quat[flowers], qvec[rows], w_old, w_new)
+            self.score[flowers] += 1
+            log_t, log_q = np.zeros_like(self.trans), np.zeros_like(self.quat)
+            log_t[flowers], log_q[flowers] = tvec[rows], qvec[rows]
+            self.all_new_trans.append(log_t)
+            self.all_new_quat.append(log_q)
+        self._append(tvec[~known], qvec[~known])
 
     def get_final_data(self):
-        score_filter = self.score > self.score_th
-        return self.trans[score_filter], self.quat[score_filter]
+        often = self.score > self.score_th
+        return self.trans[often], self.quat[often]
 
     def save_filtered_data(self, path='filtered_data.pkl'):
         with open(path, 'wb') as fp:

@@ -15,39 +15,31 @@ import numpy as np
 
 
 def squarify_bb(bb):
-    xmin, ymin, xmax, ymax = bb
-    xrange_ = xmax - xmin
-    yrange_ = ymax - ymin
-    diff = abs(xrange_ - yrange_)
-    if diff % 2 == 0:
-        decrease_min = increase_max = diff / 2
-    else:
-        decrease_min = (diff + 1) / 2
-        increase_max = (diff - 1) / 2
-    if xrange_ > yrange_:
-        ymin -= decrease_min
-        ymax += increase_max
-    elif xrange_ < yrange_:
-        xmin -= decrease_min
-        xmax += increase_max
-    return [int(xmin), int(ymin), int(xmax), int(ymax)]
+    """Grow the short side of an xyxy box to the long side, centred; an odd difference puts the extra pixel on the
+    min side.  Returns four Python ints (truncation toward zero), like the reference."""
+    x0, y0, x1, y1 = bb
+    w, h = x1 - x0, y1 - y0
+    d = abs(w - h)
+    before = (d + 1) / 2 if d % 2 else d / 2        # taken from the min coordinate
+    after = d - before                               # added to the max coordinate
+    if w > h:
+        y0, y1 = y0 - before, y1 + after
+    elif h > w:
+        x0, x1 = x0 - before, x1 + after
+    return [int(x0), int(y0), int(x1), int(y1)]
 
 
 def bb_in_frame(bb, img_shape):
-    h, w = img_shape[0], img_shape[1]
-    xmin, ymin, xmax, ymax = bb
-    if xmin < 0 or ymin < 0 or xmax > w or ymax > h:
-        return False
-    return True
+    """True when the box lies inside the (h, w, ...) image; touching the right / bottom edge is inside (slices are exclusive)."""
+    x0, y0, x1, y1 = bb
+    return not (x0 < 0 or y0 < 0 or x1 > img_shape[1] or y1 > img_shape[0])
 
 
 def filter_very_large_bb(bb_dino):
-    bb_dino = np.array(bb_dino)
-    x_range = bb_dino[:, 2] - bb_dino[:, 0]
-    y_range = bb_dino[:, 3] - bb_dino[:, 1]
-    area = x_range * y_range
-    large_area = area > 5 * np.median(area)
-    return bb_dino[np.logical_not(large_area)]
+    """Drop the boxes whose area exceeds five times the median area (GroundingDINO's whole-plant boxes)."""
+    boxes = np.array(bb_dino)
+    area = np.prod(boxes[:, 2:4] - boxes[:, 0:2], axis=1)
+    return boxes[area <= 5 * np.median(area)]
 
 
 def squarify_filter_batch(boxes, img_shape):
@@ -70,14 +62,11 @@ def nullify_yaw_batch(rotmat):
 
 
 def get_points3d(uv, Zray, K):
-    """(N,2) pixel coordinates, (N,) ray lengths in metres, (3,3) intrinsics -> (N,3) camera-frame points."""
-    uv = np.asarray(uv, dtype=np.float64)
-    N = uv.shape[0]
-    uv1 = np.hstack((uv, np.ones(N).reshape(-1, 1)))
-    xnyn1 = (np.linalg.inv(K) @ uv1.T).T
-    xnyn1_norm = np.linalg.norm(xnyn1, axis=1)
-    Z = np.asarray(Zray) / xnyn1_norm
-    return xnyn1 * Z.reshape(-1, 1)
+    """(N,2) pixel coordinates, (N,) ray lengths in metres, (3,3) intrinsics -> (N,3) camera-frame points: the pixel's
+    viewing ray K^-1 [u v 1]^T scaled to the measured length."""
+    px = np.concatenate([np.asarray(uv, dtype=np.float64), np.ones((len(uv), 1))], axis=1)
+    rays = (np.linalg.inv(K) @ px.T).T
+    return rays * (np.asarray(Zray, dtype=np.float64) / np.linalg.norm(rays, axis=1))[:, None]
 
 
 def pose_cam_to_world(obj_pose, cam_pose):
@@ -86,10 +75,10 @@ def pose_cam_to_world(obj_pose, cam_pose):
 
 
 def rot_average(quat1, quat2, weight1, weight2):
-    """Row-wise weighted average of two sets of xyzw quaternions by spherical interpolation at t = w2 / (w1 + w2)."""
-    from scipy.spatial.transform import Rotation as R, Slerp
-    avg_quat = []
-    for q1, q2, w1, w2 in zip(quat1, quat2, weight1, weight2):
-        slerp = Slerp([0, 1], R.concatenate([R.from_quat(q1), R.from_quat(q2)]))
-        avg_quat.append(slerp([w2 / (w1 + w2)]).as_quat()[0])
-    return np.array(avg_quat)
+    """Row-wise weighted mean of two sets of xyzw quaternions on the geodesic between them: the rotation a fraction
+    w2 / (w1 + w2) of the way from quat1 to quat2.  All rows at once through rotation vectors."""
+    from scipy.spatial.transform import Rotation as R
+    t = np.asarray(weight2, dtype=np.float64) / (np.asarray(weight1, dtype=np.float64) + np.asarray(weight2, dtype=np.float64))
+    start = R.from_quat(np.asarray(quat1))
+    step = (start.inv() * R.from_quat(np.asarray(quat2))).as_rotvec()
+    return (start * R.from_rotvec(step * t[:, None])).as_quat().reshape(-1, 4)

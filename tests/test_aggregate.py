@@ -63,8 +63,10 @@ def test_flower_model_tracking_matches_reference_logic(golden_dir):
     for f in range(int(t["n_frames"])):
         fm.assign_meas_to_state(t[f"m{f}"].copy())
     assert np.array_equal(fm.get_state(), t["state"]) and np.array_equal(fm.scores, t["scores"])
-    assert np.array_equal(fm.get_filtered_state(), t["kf_x"])
-    assert np.array_equal(np.array([k.P for k in fm.kfs]), t["kf_P"])
+    # association, update order and scores are exact; the stacked 7x7 updates differ from the reference's one-filter-at-a-time
+    # arithmetic only in the last bits (different BLAS calls for the same products)
+    assert np.allclose(fm.get_filtered_state(), t["kf_x"], rtol=0, atol=1e-12)
+    assert np.allclose(np.array([k.P for k in fm.kfs]), t["kf_P"], rtol=0, atol=1e-12)
     assert np.allclose(np.linalg.norm(fm.get_filtered_state()[:, 3:], axis=1), 1.0)
     assert fm.scores.max() > 3 and len(fm.kfs) >= 9
 
