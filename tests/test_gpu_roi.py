@@ -183,3 +183,38 @@ def test_roi_1080p_last_frames_of_64(cuda_lib, interp, size):
         want = R.crop_batch_reference(frames[f - 61], masks[f - 61], [bb], size=size, interp=interp)[0]
         assert np.array_equal(got[i], want), (i, f, bb)
     e.close()
+
+
+@pytest.mark.parametrize("interp,size,n_boxes", [(R.BILINEAR, 224, 160), (R.LANCZOS4, 224, 96), (R.LANCZOS4, 512, 40), (R.BILINEAR, 512, 40),
+                                                  (R.BILINEAR, 96, 64), (R.LANCZOS4, 160, 48)])
+def test_roi_random_boxes_and_alignments_bit_exact(cuda_lib, interp, size, n_boxes):
+    """Random square boxes of every size and position (all 16-byte phases of the row segments, boxes touching every
+    edge, sides from 1 px to the whole frame height, up- and down-scaling by more than 2x) in two frames of different
+    widths, the second one addressed through a non-zero frame index: bit-exact against cv2, with and without mask."""
+    rng = np.random.default_rng(1000 + size + interp)
+    for H, W in ((300, 480), (200, 272)):
+        frames = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+        masks = np.zeros((2, H, W), np.uint8)
+        yy, xx = np.ogrid[0:H, 0:W]
+        masks[0][((xx - W / 2) / (W / 2.5)) ** 2 + ((yy - H / 2) / (H / 2.2)) ** 2 <= 1] = 255
+        masks[1] = rng.integers(0, 2, (H, W), dtype=np.uint8) * 255                       # worst case: noise mask, all partial
+        side = np.concatenate([rng.integers(1, 9, n_boxes // 4), rng.integers(9, H + 1, n_boxes - n_boxes // 4)])
+        side[-1] = H
+        x0 = (rng.random(n_boxes) * (W - side + 1)).astype(np.int64)
+        y0 = (rng.random(n_boxes) * (H - side + 1)).astype(np.int64)
+        x0[::7] = 0; y0[::5] = 0
+        x0[3::11] = (W - side)[3::11]; y0[4::13] = (H - side)[4::13]
+        f = rng.integers(0, 2, n_boxes)
+        b5 = np.stack([f, x0, y0, x0 + side, y0 + side], 1).astype(np.int32)
+        e = cuda_lib.Engine(0, max_batch=8, crop_hw=size)
+        try:
+            fr, mk = torch.from_numpy(frames).cuda(), torch.from_numpy(masks).cuda()
+            for m_dev, with_mask in ((mk, True), (None, False)):
+                got = e.roi_crop(fr, m_dev, b5, size, interp)
+                torch.cuda.synchronize()
+                got = got.cpu().numpy()
+                for i, (fi, *bb) in enumerate(b5):
+                    want = R.crop_batch_reference(frames[fi], masks[fi] if with_mask else None, [bb], size=size, interp=interp)[0]
+                    assert np.array_equal(got[i], want), (H, W, with_mask, i, fi, bb)
+        finally:
+            e.close()
