@@ -311,8 +311,16 @@ __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, 
                                           uint32_t plane_bytes, uint32_t lut) {
   uint32_t o[3];
   if (HAS_MASK && __any_sync(0xFFFFFFFFu, m4 - (base4 + 4u) < 1016u)) {
+    // normalise_u8(v, m) on X = (4v)(4m) = 16 v m: every step of normalise_u8 scales by an exact power of two
+    // (q = fl(X r / 16) = fl(v m r), e = fma(-q, 16 * 65025, X) = 16 e0, fma(e, r / 16, q)): bit-identical, no shifts
+    const uint32_t mm = m4 & 0x3FCu;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) o[c] = __float_as_uint(normalise_u8((int)((v4[c] >> 2) & 0xFFu), (int)((m4 >> 2) & 0xFFu)));
+    for (int c = 0; c < 3; ++c) {
+      const float x = (float)((v4[c] & 0x3FCu) * mm);
+      const float r16 = (1.0f / 65025.0f) * 0.0625f;
+      const float q = x * r16;
+      o[c] = __float_as_uint(fmaf(fmaf(-q, 16.0f * 65025.0f, x), r16, q));
+    }
   } else {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -352,25 +360,23 @@ struct R3Col2 {
 // Horizontally filtered source row for cv2's vertical pass, which consumes A = S >> 4 (S = a0 * p0 + a1 * p1 < 2^20).
 // The vertical pass runs on the FMA pipe (see r3_emit2), so the value is kept as the float 2^23 + 16 * A: its bit
 // pattern is 0x4B000000 | (S & ~15), one logic operation on the DP2A result.
-__device__ __forceinline__ uint32_t r3_f16a(uint32_t S) {
+__device__ __forceinline__ uint32_t r3_f16a(uint32_t S, uint32_t k23) {      // k23 = 0x4B000000, kept in a register by the caller
   uint32_t d;
-  asm("lop3.b32 %0, %1, 0xFFFFF0, %2, 0xEA;" : "=r"(d) : "r"(S), "r"(0x4B000000u));
+  asm("lop3.b32 %0, %1, 0xFFFFF0, %2, 0xEA;" : "=r"(d) : "r"(S), "r"(k23));
   return d;
 }
 template <bool HAS_MASK>
-__device__ __forceinline__ void r3_hfilt2(uint32_t row, const R3Col2& k, uint32_t (&dst)[HAS_MASK ? 4 : 3]) {
-  const uint32_t wa = row + k.iofs;
+__device__ __forceinline__ void r3_hfilt2(uint32_t wa, uint32_t ma, const R3Col2& k, uint32_t k23, uint32_t (&dst)[HAS_MASK ? 4 : 3]) {
   const uint32_t w0 = r3_lds32(wa), w1 = r3_lds32(wa + 4), w2 = r3_lds32(wa + 8);
   const uint32_t u0 = __funnelshift_r(w0, w1, k.ish), u1 = __funnelshift_r(w1, w2, k.ish);   // a0 a1 a2 b0 | b1 b2 . .
   const uint32_t r1 = __byte_perm(u0, u1, 0x4130);                                           // a0 b0 a1 b1
   const uint32_t r2 = __byte_perm(u0, u1, 0x0052);                                           // a2 b2 . .
-  dst[0] = r3_f16a(__dp2a_lo(k.cx, r1, 0u));
-  dst[1] = r3_f16a(__dp2a_hi(k.cx, r1, 0u));
-  dst[2] = r3_f16a(__dp2a_lo(k.cx, r2, 0u));
+  dst[0] = r3_f16a(__dp2a_lo(k.cx, r1, 0u), k23);
+  dst[1] = r3_f16a(__dp2a_hi(k.cx, r1, 0u), k23);
+  dst[2] = r3_f16a(__dp2a_lo(k.cx, r2, 0u), k23);
   if (HAS_MASK) {
-    const uint32_t ma = row + k.mofs;
     const uint32_t r3 = __byte_perm(r3_lds32(ma), r3_lds32(ma + 4), k.msel);
-    dst[HAS_MASK ? 3 : 0] = r3_f16a(__dp2a_lo(k.cx, r3, 0u));
+    dst[HAS_MASK ? 3 : 0] = r3_f16a(__dp2a_lo(k.cx, r3, 0u), k23);
   }
 }
 // One output pixel.  cv2's vertical pass is ((b0 * A0 >> 16) + (b1 * A1 >> 16) + 2) >> 2 with two separate truncations.
@@ -419,6 +425,8 @@ __device__ __forceinline__ void r3_consumer2(const Roi3Params& p, uint32_t sb, i
   }
   const long long crop_bytes = FMT == 0 ? 3LL * S * S * 4 : (long long)p.g.Hp * p.g.Wp * 16;
   const int col_bytes = FMT == 0 ? 4 : 8;
+  uint32_t k23;                              // the bit pattern of 2^23, opaque to ptxas so that it stays in a register
+  asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(k23));
   for (int it = 0;; ++it) {
     const int b = it & 1;
     r3_bar_wait(sb + kR3ItemFull + 8 * b, ((uint32_t)it >> 1) & 1u);
@@ -434,6 +442,7 @@ __device__ __forceinline__ void r3_consumer2(const Roi3Params& p, uint32_t sb, i
       col.iofs = e.x & 0xFFFFu; col.ish = e.x >> 16; col.cx = e.y; col.mofs = e.z & 0xFFFFu; col.msel = e.z >> 16;
     }
     uint8_t* out = out0 + (int)h0.y * crop_bytes + (int)h1.z * col_bytes;
+    asm volatile("" : "+l"(out));            // one 64-bit register pair: the emit adds the row offset to it, nothing else
     uint32_t A[NCH], B[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) A[j] = B[j] = 0u;
@@ -443,22 +452,23 @@ __device__ __forceinline__ void r3_consumer2(const Roi3Params& p, uint32_t sb, i
       const int k_this = imin(K, rows_left);
       rows_left -= k_this;
       r3_bar_wait(full, sphase);
-      uint32_t row = stage_row;
-      for (int k = 0; k < k_this; k += 2) {
-        r3_hfilt2<HAS_MASK>(row, col, A);
+      uint32_t wa = stage_row + col.iofs, ma = stage_row + col.mofs;      // this column's words in the current row
+      const int u_end = u + k_this;
+      while (u != u_end) {
+        r3_hfilt2<HAS_MASK>(wa, ma, col, k23, A);
         while ((int)yt.x == u) {             // output rows whose upper source row is u
           r3_emit2<HAS_MASK, FMT>(B, A, yt, out, plane_bytes, lut);
           ya += kR3YtabEntry2;
           yt = r3_lds128(ya);
         }
-        ++u; row += pitch;
-        r3_hfilt2<HAS_MASK>(row, col, B);
+        ++u; wa += pitch; ma += pitch;
+        r3_hfilt2<HAS_MASK>(wa, ma, col, k23, B);
         while ((int)yt.x == u) {
           r3_emit2<HAS_MASK, FMT>(A, B, yt, out, plane_bytes, lut);
           ya += kR3YtabEntry2;
           yt = r3_lds128(ya);
         }
-        ++u; row += pitch;
+        ++u; wa += pitch; ma += pitch;
       }
       __syncwarp();
       if (lane == 0) r3_bar_arrive(full + kR3Empty);
