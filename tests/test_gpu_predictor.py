@@ -78,3 +78,29 @@ def test_detection_txt_format(tmp_path, net):
     assert rows.shape == (2, 15)
     assert np.allclose(rows[0, :6], [10, 20, 110, 121, 60, 70.5])
     assert open(p).read().split()[0] == "10.0000000"
+
+
+def test_bulk_inference_over_an_image_folder(tmp_path, net):
+    """flope_b200.bulk_infer: images + detector boxes (+ masks) on disk -> detection/*.txt, the PoseNet half of
+    scripts/test_posenet.py:62-161, against the oracle pipeline (raw Procrustes rotations, '%.7f' rows)."""
+    import cv2
+    from flope_b200 import bulk_infer
+    from flope_b200.aggregate import read_detection_txt
+    frames, masks, det = synth.frames_and_boxes(3, 5, H=360, W=640, seed=31, smooth=True)
+    det[2, 0] = [600, 10, 640, 200]                      # squarified box leaves the frame: dropped
+    for d in ("rgb", "boxes", "masks"):
+        (tmp_path / d).mkdir()
+    for i in range(3):
+        cv2.imwrite(str(tmp_path / "rgb" / f"{i:06d}.png"), frames[i])
+        cv2.imwrite(str(tmp_path / "masks" / f"{i:06d}.png"), masks[i])
+        np.savetxt(str(tmp_path / "boxes" / f"{i:06d}.txt"), det[i].astype(np.float64) if i else np.zeros((0, 4)))
+    n_img, n_fl = bulk_infer.run(str(tmp_path / "rgb"), str(tmp_path / "boxes"), str(tmp_path / "det"), str(tmp_path / "masks"),
+                                 state_dict=net.state_dict(), crop=224, interp="linear", frames_per_batch=2)
+    assert n_img == 3
+    assert (tmp_path / "det" / "000000.txt").read_text() == ""                  # no boxes: empty file, like the reference
+    for i in (1, 2):
+        want = opipe.run(net, frames[i], masks[i], det[i], size=224, interp=ores.BILINEAR, nullify_yaw=False)
+        bbox, uv, rot = read_detection_txt(str(tmp_path / "det" / f"{i:06d}.txt"))
+        assert np.array_equal(bbox, det[i][want["keep"]].astype(np.int16))
+        assert orot.geodesic_deg(rot.reshape(-1, 3, 3), want["rot"]).mean() <= 0.5
+    assert n_fl == 5 + 4
