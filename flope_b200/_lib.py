@@ -19,7 +19,7 @@ SYMBOLS = [
     "flope_version", "flope_last_error", "flope_engine_create", "flope_engine_destroy",
     "flope_engine_load_weights", "flope_squarify_filter", "flope_roi_crop", "flope_posenet_forward",
     "flope_pose_head", "flope_nullify_yaw", "flope_infer_frames", "flope_engine_last_launches",
-    "flope_debug_activation", "flope_debug_normalise_lut", "flope_debug_set", "flope_engine_set_schedule", "flope_debug_timeline", "flope_ingest_crops",
+    "flope_debug_activation", "flope_debug_normalise_lut", "flope_debug_set", "flope_engine_set_schedule", "flope_pack_boxes", "flope_debug_timeline", "flope_ingest_crops",
     "flope_engine_profile", "flope_engine_profile_read", "flope_depth_values", "flope_yolo_mask",
 ]
 
@@ -62,6 +62,7 @@ def lib():
         L.flope_debug_normalise_lut.argtypes = [C.c_void_p, C.c_void_p]
         L.flope_debug_set.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.flope_engine_set_schedule.argtypes = [C.c_void_p, C.c_int]
+        L.flope_pack_boxes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.flope_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.flope_engine_profile.argtypes = [C.c_void_p, C.c_int]
         L.flope_engine_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.c_int]
@@ -88,6 +89,13 @@ def squarify_filter(boxes_i32, H, W):
     check(lib().flope_squarify_filter(boxes_i32.ctypes.data, n, H, W, sq.ctypes.data, keep.ctypes.data))
     keep = keep.astype(bool)
     return sq[keep], keep
+
+
+def pack_boxes(img, boxes_xyxy, slot_h, slot_w, out):
+    """Host: copy the box regions of a contiguous uint8 (H,W[,ch]) numpy image into the slots of `out` (n,slot_h,slot_w[,ch])."""
+    ch = img.shape[2] if img.ndim == 3 else 1
+    check(lib().flope_pack_boxes(img.ctypes.data, img.shape[0], img.shape[1], ch, boxes_xyxy.ctypes.data, boxes_xyxy.shape[0],
+                                 int(slot_h), int(slot_w), out.ctypes.data))
 
 
 def _stream(device=None):

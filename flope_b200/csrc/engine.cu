@@ -1118,6 +1118,19 @@ int flope_squarify_filter(const int32_t* boxes, int n, int H, int W, int32_t* ou
   return FLOPE_OK;
 }
 
+int flope_pack_boxes(const uint8_t* img, int H, int W, int ch, const int32_t* boxes, int n, int slot_h, int slot_w, uint8_t* out) {
+  if (n < 0 || ch < 1 || (n > 0 && (!img || !boxes || !out))) return fail(FLOPE_EINVAL, "bad argument");
+  for (int i = 0; i < n; ++i) {
+    const int x0 = boxes[4 * i], y0 = boxes[4 * i + 1], x1 = boxes[4 * i + 2], y1 = boxes[4 * i + 3];
+    if (x0 < 0 || y0 < 0 || x1 > W || y1 > H || x1 <= x0 || y1 <= y0 || x1 - x0 > slot_w || y1 - y0 > slot_h)
+      return fail(FLOPE_EINVAL, "box outside the image or larger than the slot");
+    const size_t row = (size_t)(x1 - x0) * ch;
+    uint8_t* dst = out + (size_t)i * slot_h * slot_w * ch;
+    for (int y = y0; y < y1; ++y) std::memcpy(dst + (size_t)(y - y0) * slot_w * ch, img + ((size_t)y * W + x0) * ch, row);
+  }
+  return FLOPE_OK;
+}
+
 int flope_roi_crop(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W, int64_t frame_stride,
                    const uint8_t* d_masks, const int32_t* d_boxes, int n, int S, int interp, void* d_out, int out_fmt,
                    void* stream) {

@@ -121,6 +121,50 @@ class _PredictorBase:
             Rt[:, :3, 3] = xyz
         return Rt
 
+    PACK_BOXES = True               # upload the box regions instead of the frame when they are a fraction of it
+
+    def _packed_upload(self, rgb, mask, sq_bb):
+        """A handful of flowers per frame (scripts/live_pose.py): the boxes cover a fraction of the frame, and a
+        pageable 6 MB frame upload costs more than the whole device pipeline.  Pack the box regions into fixed-size
+        slots of one pinned arena on the host (flope_pack_boxes: row memcpys), upload the arena with ONE copy and run
+        the same ROI kernel on it - every slot is a small "frame" with its box at the origin, so the crops are bit-identical.
+        Returns (frames (n,sh,sw,3), masks (n,sh,sw) or None, boxes5 (n,5)) on the device, or None to take the full-frame path."""
+        if not self.PACK_BOXES or torch.is_tensor(mask) or not isinstance(rgb, np.ndarray) or rgb.dtype != np.uint8 or rgb.ndim != 3:
+            return None
+        n = sq_bb.shape[0]
+        sides = np.maximum(sq_bb[:, 2] - sq_bb[:, 0], sq_bb[:, 3] - sq_bb[:, 1])
+        sh = int(sides.max())
+        sw = (sh + 15) & ~15
+        H, W = rgb.shape[:2]
+        if 2 * n * sh * sw > H * W:                     # many or large boxes: the frame is the smaller upload
+            return None
+        has_mask = mask is not None
+        if has_mask:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        fb, mb = n * sh * sw * 3, (n * sh * sw if has_mask else 0)
+        total = fb + mb + n * 20
+        arena = getattr(self, "_arena", None)
+        if arena is None or arena[0].numel() < total:
+            cap = max(total, 1 << 20)
+            arena = (torch.empty(cap, dtype=torch.uint8).pin_memory(), torch.empty(cap, dtype=torch.uint8, device=self.device))
+            self._arena = arena
+        host, dev = arena
+        hn = host.numpy()
+        bx = np.ascontiguousarray(sq_bb, dtype=np.int32)
+        _lib.pack_boxes(np.ascontiguousarray(rgb), bx, sh, sw, hn[:fb])
+        if has_mask:
+            _lib.pack_boxes(mask, bx, sh, sw, hn[fb:fb + mb])
+        b5 = np.zeros((n, 5), np.int32)
+        b5[:, 0] = np.arange(n)
+        b5[:, 3] = bx[:, 2] - bx[:, 0]
+        b5[:, 4] = bx[:, 3] - bx[:, 1]
+        hn[fb + mb:total] = np.frombuffer(b5.tobytes(), np.uint8)
+        with torch.cuda.device(self.device):
+            dev[:total].copy_(host[:total], non_blocking=True)
+        frames = dev[:fb].view(n, sh, sw, 3)
+        masks = dev[fb:fb + mb].view(n, sh, sw) if has_mask else None
+        return frames, masks, dev[fb + mb:total].view(torch.int32).view(n, 5)
+
     def poses_from_boxes(self, rgb, mask, sq_bb, nullify_yaw=True):
         """uint8 frame (H,W,3) + mask (H,W) or None + square in-frame boxes (N,4) -> rotations (N,3,3).
 
@@ -132,6 +176,12 @@ class _PredictorBase:
         if (sq_bb[:, 2] <= sq_bb[:, 0]).any() or (sq_bb[:, 3] <= sq_bb[:, 1]).any():
             # the reference hands such a slice to cv2.resize, which raises (pose_predictor.py:145)
             raise ValueError("empty box (xmax <= xmin or ymax <= ymin) after squarify")
+        packed = self._packed_upload(rgb, mask, sq_bb)
+        if packed is not None:
+            frame, msk, b5 = packed
+            with torch.cuda.device(self.device):
+                _, R, Ry = eng.infer_frames(frame, msk, b5, self.interp, want_R=not nullify_yaw, want_yaw=nullify_yaw)
+                return (Ry if nullify_yaw else R).cpu().numpy()
         with torch.cuda.device(self.device):
             frame = torch.from_numpy(np.ascontiguousarray(rgb, dtype=np.uint8)).to(self.device, non_blocking=True)[None]
             if mask is None:

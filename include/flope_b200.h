@@ -185,6 +185,13 @@ int flope_debug_normalise_lut(float* d_out, void* stream);
  *   "fc_small"    0/1  fc GEMM on 128-crop x 64-channel single-CTA tiles instead of 256 x 128 (default 1)
  * "pair", "small_tiles" and "fc_small" change the packed-weight layout: call flope_engine_load_weights again afterwards.
  * Activation names for flope_debug_activation additionally include "x0" (the stem's space-to-depth input). */
+/* Host helper of the predictors (no reference counterpart: the reference slices the numpy frame per box,
+ * pose_predictor.py:141-143): copy the n box regions of a host (H,W,ch) uint8 image into n fixed-size slots of
+ * slot_h x slot_w x ch bytes each, box i at the origin of slot i.  With a handful of flowers per frame the boxes are a
+ * fraction of the frame, so the predictor uploads the packed slots (as n small "frames", boxes (i,0,0,s,s)) instead of the
+ * whole frame.  Bytes of a slot outside its box are left as they are.  boxes: n x 4 xyxy, in-frame, sides <= slot_h, slot_w. */
+int flope_pack_boxes(const uint8_t* img, int H, int W, int ch, const int32_t* boxes_xyxy, int n, int slot_h, int slot_w,
+                     uint8_t* out);
 int flope_debug_set(flope_engine* e, const char* key, int value);
 /* How the backbone of this engine is launched (FLOPE_SCHED_*); see the concurrency paragraph at the top.  Product
  * option (flope_b200.pipeline.EnginePool uses it), cheap: it only drops the engine's captured CUDA graphs. */

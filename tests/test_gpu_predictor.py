@@ -104,3 +104,25 @@ def test_bulk_inference_over_an_image_folder(tmp_path, net):
         assert np.array_equal(bbox, det[i][want["keep"]].astype(np.int16))
         assert orot.geodesic_deg(rot.reshape(-1, 3, 3), want["rot"]).mean() <= 0.5
     assert n_fl == 5 + 4
+
+
+@pytest.mark.parametrize("crop_hw,interp", [(224, ores.BILINEAR), (224, ores.LANCZOS4)])
+def test_packed_box_upload_equals_full_frame_upload(net, crop_hw, interp):
+    """A few flowers in a 1080p frame: the predictor uploads the packed box regions (flope_pack_boxes) instead of the
+    frame.  Same kernels on the same pixels: the poses must be bit-identical to the full-frame path, with and without mask."""
+    from flope_b200.posenet import PoseResNet
+    from flope_b200.predictor import FastPosePredictor
+    frames, masks, det = synth.frames_and_boxes(1, 6, seed=41, with_mask=True)
+    m = PoseResNet(device="cuda:0", max_batch=8, crop_hw=crop_hw)
+    m.load_state_dict(net.state_dict())
+    for mask in (masks[0], None):
+        pred = FastPosePredictor("cuda:0", detector=lambda rgb: (det[0].astype(np.int16), mask), posenet=m, crop_hw=crop_hw,
+                                 interp=interp)
+        assert pred._packed_upload(frames[0], mask, np.array([[0, 0, 100, 100]], np.int32)) is not None
+        a = pred.get_flower_poses(frames[0], None)
+        pred.PACK_BOXES = False
+        b = pred.get_flower_poses(frames[0], None)
+        assert a.shape == (6, 4, 4) and np.array_equal(a, b)
+    many = np.tile(np.array([[0, 0, 600, 600]], np.int32), (8, 1))          # boxes larger than half the frame in total: full-frame path
+    pred.PACK_BOXES = True
+    assert pred._packed_upload(frames[0], None, many) is None
