@@ -581,6 +581,7 @@ __device__ __forceinline__ void r3_consumer8(const Roi3Params& p, uint32_t sb, i
       patch_r = __any_sync(0xFFFFFFFFu, e0.z & 2u);
     }
     uint8_t* out = out0 + (int)h0.y * crop_bytes + (int)h1.z * col_bytes;
+    asm volatile("" : "+l"(out));
     int R[8][NCH];                           // ring: slot (u & 7) holds filtered source row u
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -616,7 +617,7 @@ __device__ __forceinline__ void r3_consumer8(const Roi3Params& p, uint32_t sb, i
             int acc = 1 << 21;
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc += R[i][j] * cf[i];
-            return (uint32_t)iclamp(acc >> 20, 0, 1023);
+            return (uint32_t)__vimin_s32_relu(acc >> 20, 1023);        // max(min(x, 1023), 0) in one VIMNMX.RELU
           };
           const uint32_t m4 = HAS_MASK ? vpass(NCH - 1) : 1020u;
           const bool off = HAS_MASK && m4 < 4u;
