@@ -483,7 +483,7 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
 int build_network(flope_engine* e) {
   const int S = e->S;
   const int s2 = S / 2, s4 = S / 4;
-  e->buf_x0 = add_buf(e, 16, s2, s2, 2, false, nullptr);
+  e->buf_x0 = add_buf(e, 16, s2, s2, 2, false, "x0");
   e->buf_stem = add_buf(e, 64, s2, s2, 1, false, "stem");
   int cur = add_buf(e, 64, s4, s4, 1, false, "maxpool");
   e->buf_mp_out = cur;

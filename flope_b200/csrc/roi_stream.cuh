@@ -304,22 +304,32 @@ __device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, in
 // value of m4's bits above bit 9 (compares run on the raw words).
 //   fmt 1: two 32-bit words [c0 c1 | c2 0] of bf16;  bf16_rn(fl(4v * fl(1/1020))) == bf16_rn(fp32(v / 255)) for all v
 //   fmt 0: three fp32 words; unmasked values come from the 256-entry table in shared memory
-// The branch is warp-uniform (a vote): a warp with a partially masked pixel (mask edge) takes the general
+// fp32 output: the branch is warp-uniform (a vote) - a warp with a partially masked pixel (mask edge) takes the general
 // quotient for every lane, everything else takes the unmasked path and zeroes its masked-out lanes with a select.
 template <bool HAS_MASK, int FMT>
 __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, uint32_t base4, bool off, uint8_t* q,
                                           uint32_t plane_bytes, uint32_t lut) {
   uint32_t o[3];
-  if (HAS_MASK && __any_sync(0xFFFFFFFFu, m4 - (base4 + 4u) < 1016u)) {
-    // normalise_u8(v, m) on X = (4v)(4m) = 16 v m: every step of normalise_u8 scales by an exact power of two
-    // (q = fl(X r / 16) = fl(v m r), e = fma(-q, 16 * 65025, X) = 16 e0, fma(e, r / 16, q)): bit-identical, no shifts
+  if (FMT == 1 && HAS_MASK) {
+    // bf16 output with a mask: ONE branch-free expression for every pixel.  bf16_rn(fl(float(v m) * fl(1/65025))) equals
+    // bf16_rn of the reference's float32((v * (m / 255.0)) / 255.0) for all 65 536 (v, m) pairs (the fp32 quotient itself
+    // differs in 1 066 of them, always below bf16 resolution; tests/test_gpu_roi.py checks the device exhaustively), so
+    // the two correction FMAs of normalise_u8 are not needed here, m = 0 gives exactly 0 and m = 255 the unmasked value:
+    // no vote, no select, and every warp of a strip does the same work whether the mask edge crosses it or not.
+    const uint32_t mm = m4 & 0x3FCu;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)      // X = (4v)(4m) = 16 v m < 2^20: exact in fp32; the 1/16 is folded into the constant
+      o[c] = __float_as_uint((float)((v4[c] & 0x3FCu) * mm) * ((1.0f / 65025.0f) * 0.0625f));
+  } else if (HAS_MASK && __any_sync(0xFFFFFFFFu, m4 - (base4 + 4u) < 1016u)) {
+    // fp32 output, a partially masked pixel in the warp: the exact quotient normalise_u8(v, m) for every lane, on
+    // X = 16 v m (each step of normalise_u8 scales by an exact power of two: bit-identical, no shifts)
     const uint32_t mm = m4 & 0x3FCu;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float x = (float)((v4[c] & 0x3FCu) * mm);
       const float r16 = (1.0f / 65025.0f) * 0.0625f;
-      const float q = x * r16;
-      o[c] = __float_as_uint(fmaf(fmaf(-q, 16.0f * 65025.0f, x), r16, q));
+      const float qq = x * r16;
+      o[c] = __float_as_uint(fmaf(fmaf(-qq, 16.0f * 65025.0f, x), r16, qq));
     }
   } else {
 #pragma unroll
@@ -343,10 +353,10 @@ __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, 
     uint2 v;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(v.x) : "f"(__uint_as_float(o[1])), "f"(__uint_as_float(o[0])));
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(v.y) : "f"(0.f), "f"(__uint_as_float(o[2])));
-    if (HAS_MASK) { v.x = off ? 0u : v.x; v.y = off ? 0u : v.y; }
     *reinterpret_cast<uint2*>(q) = v;
   }
 }
+
 // ---------------------------------------------------------------------------------------------
 // bilinear consumer
 // ---------------------------------------------------------------------------------------------

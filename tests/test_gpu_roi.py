@@ -218,3 +218,35 @@ def test_roi_random_boxes_and_alignments_bit_exact(cuda_lib, interp, size, n_box
                     assert np.array_equal(got[i], want), (H, W, with_mask, i, fi, bb)
         finally:
             e.close()
+
+
+@pytest.mark.parametrize("interp", [R.BILINEAR, R.LANCZOS4])
+def test_engine_format_masked_normalise_exhaustive(cuda_lib, interp):
+    """The bf16 stem-input crops use one branch-free expression for every (value, mask) pair.  A 256 x 256 box resized to
+    256 x 256 is the identity for both interpolation modes (coefficients 2048 / 0), so with img[y][x] = x and
+    mask[y][x] = y the crop holds all 65 536 pairs: every stored bf16 must equal bf16_rn of the reference's float32
+    expression (oracle.resize.normalise_lut)."""
+    S = 256
+    frame = np.broadcast_to(np.arange(S, dtype=np.uint8)[None, :, None], (S, S, 3)).copy()
+    mask = np.broadcast_to(np.arange(S, dtype=np.uint8)[:, None], (S, S)).copy()
+    e = cuda_lib.Engine(0, max_batch=1, crop_hw=S)
+    try:
+        b5 = np.array([[0, 0, 0, S, S]], np.int32)
+        f32 = e.roi_crop(torch.from_numpy(frame).cuda()[None], torch.from_numpy(mask).cuda()[None], b5, S, interp)
+        e.roi_crop(torch.from_numpy(frame).cuda()[None], torch.from_numpy(mask).cuda()[None], b5, S, interp, out_fmt=cuda_lib.OUT_ENGINE)
+        buf, chw = e.debug_activation("x0", 1)
+        torch.cuda.synchronize()
+        lut = R.normalise_lut()                                                # [img][mask] float32
+        want = lut[np.arange(S)[None, :], np.arange(S)[:, None]]               # [y][x] = lut[img = x][mask = y]
+        assert np.array_equal(f32.cpu().numpy()[0, 0], want)                   # the fp32 path is exact as ever
+        x0 = buf.cpu().numpy().reshape(16, S // 2, S // 2)                     # channel k = (y & 1) * 8 + (x & 1) * 4 + c
+        want_bf16 = torch.from_numpy(want).to(torch.bfloat16).to(torch.float32).numpy()
+        for c in range(3):
+            got = np.empty((S, S), np.float32)
+            for by in range(2):
+                for bx in range(2):
+                    got[by::2, bx::2] = x0[by * 8 + bx * 4 + c]
+            assert np.array_equal(got, want_bf16), (interp, c, int((got != want_bf16).sum()))
+        assert not x0[3::4].any()                                              # the pad lane of every pixel stays zero
+    finally:
+        e.close()
