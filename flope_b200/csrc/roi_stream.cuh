@@ -308,18 +308,27 @@ __device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, in
 // quotient for every lane, everything else takes the unmasked path and zeroes its masked-out lanes with a select.
 template <bool HAS_MASK, int FMT>
 __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, uint32_t base4, bool off, uint8_t* q,
-                                          uint32_t plane_bytes, uint32_t lut) {
+                                          uint32_t plane_bytes, uint32_t lut, uint32_t k23) {
   uint32_t o[3];
   if (FMT == 1 && HAS_MASK) {
-    // bf16 output with a mask: ONE branch-free expression for every pixel.  bf16_rn(fl(float(v m) * fl(1/65025))) equals
-    // bf16_rn of the reference's float32((v * (m / 255.0)) / 255.0) for all 65 536 (v, m) pairs (the fp32 quotient itself
-    // differs in 1 066 of them, always below bf16 resolution; tests/test_gpu_roi.py checks the device exhaustively), so
-    // the two correction FMAs of normalise_u8 are not needed here, m = 0 gives exactly 0 and m = 255 the unmasked value:
-    // no vote, no select, and every warp of a strip does the same work whether the mask edge crosses it or not.
-    const uint32_t mm = m4 & 0x3FCu;
+    // bf16 output with a mask: ONE branch-free expression for every pixel, two instructions per channel.
+    //   mr  = fl(4m * R),  R = fl(1/65025) / 16          (one FFMA on the 2^23 + 4m bit pattern)
+    //   out = fl(4v * mr)                                 (one FFMA on the 2^23 + 4v bit pattern: (2^23 + 4v) mr - 2^23 mr, exact, one rounding)
+    // bf16_rn(out) equals bf16_rn of the reference's float32((v * (m / 255.0)) / 255.0) for all 65 536 (v, m) pairs (the
+    // fp32 values themselves differ below bf16 resolution; tests/test_gpu_roi.py checks the device exhaustively), m = 0
+    // gives exactly 0 and m = 255 the unmasked value: no vote, no select, and every warp of a strip does the same work
+    // whether the mask edge crosses it or not.
+    constexpr float R = (1.0f / 65025.0f) * 0.0625f;
+    uint32_t mb;
+    asm("lop3.b32 %0, %1, 0x3FC, %2, 0xEA;" : "=r"(mb) : "r"(m4), "r"(k23));
+    const float mr = fmaf(__uint_as_float(mb), R, -8388608.0f * R);
+    const float cc = mr * -8388608.0f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)      // X = (4v)(4m) = 16 v m < 2^20: exact in fp32; the 1/16 is folded into the constant
-      o[c] = __float_as_uint((float)((v4[c] & 0x3FCu) * mm) * ((1.0f / 65025.0f) * 0.0625f));
+    for (int c = 0; c < 3; ++c) {
+      uint32_t vb;
+      asm("lop3.b32 %0, %1, 0x3FC, %2, 0xEA;" : "=r"(vb) : "r"(v4[c]), "r"(k23));
+      o[c] = __float_as_uint(fmaf(__uint_as_float(vb), mr, cc));
+    }
   } else if (HAS_MASK && __any_sync(0xFFFFFFFFu, m4 - (base4 + 4u) < 1016u)) {
     // fp32 output, a partially masked pixel in the warp: the exact quotient normalise_u8(v, m) for every lane, on
     // X = 16 v m (each step of normalise_u8 scales by an exact power of two: bit-identical, no shifts)
@@ -339,7 +348,7 @@ __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, 
       } else {
         // (float)(4v) without a conversion: the integer sits in the mantissa of 2^23 + 4v
         uint32_t xb;
-        asm("lop3.b32 %0, %1, 0x3FC, %2, 0xEA;" : "=r"(xb) : "r"(v4[c]), "r"(0x4B000000u));
+        asm("lop3.b32 %0, %1, 0x3FC, %2, 0xEA;" : "=r"(xb) : "r"(v4[c]), "r"(k23));
         o[c] = __float_as_uint(fmaf(__uint_as_float(xb), 1.0f / 1020.0f, -8388608.0f * (1.0f / 1020.0f)));
       }
       if (FMT == 0 && HAS_MASK) o[c] = off ? 0u : o[c];
@@ -401,7 +410,7 @@ __device__ __forceinline__ float r3_fma_rm(float a, float b, float c) {
 }
 template <bool HAS_MASK, int FMT>
 __device__ __forceinline__ void r3_emit2(const uint32_t (&lo)[HAS_MASK ? 4 : 3], const uint32_t (&up)[HAS_MASK ? 4 : 3],
-                                         const U32x4& yt, uint8_t* out, uint32_t plane_bytes, uint32_t lut) {
+                                         const U32x4& yt, uint8_t* out, uint32_t plane_bytes, uint32_t lut, uint32_t k23) {
   constexpr int NCH = HAS_MASK ? 4 : 3;
   constexpr uint32_t kBase = 0x4B400000u;    // 1.5 * 2^23
   const float b0 = __uint_as_float(yt.y), b1 = __uint_as_float(yt.z);
@@ -414,7 +423,7 @@ __device__ __forceinline__ void r3_emit2(const uint32_t (&lo)[HAS_MASK ? 4 : 3],
   uint32_t v4[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) v4[j] = __float_as_uint(r3_fma_rm(b1, __uint_as_float(up[j]), r3_fma_rm(b0, __uint_as_float(lo[j]), m0)));
-  r3_finish<HAS_MASK, FMT>(v4, m4, kBase, off, out + yt.w, plane_bytes, lut);
+  r3_finish<HAS_MASK, FMT>(v4, m4, kBase, off, out + yt.w, plane_bytes, lut, k23);
 }
 
 template <bool HAS_MASK, int FMT>
@@ -467,14 +476,14 @@ __device__ __forceinline__ void r3_consumer2(const Roi3Params& p, uint32_t sb, i
       while (u != u_end) {
         r3_hfilt2<HAS_MASK>(wa, ma, col, k23, A);
         while ((int)yt.x == u) {             // output rows whose upper source row is u
-          r3_emit2<HAS_MASK, FMT>(B, A, yt, out, plane_bytes, lut);
+          r3_emit2<HAS_MASK, FMT>(B, A, yt, out, plane_bytes, lut, k23);
           ya += kR3YtabEntry2;
           yt = r3_lds128(ya);
         }
         ++u; wa += pitch; ma += pitch;
         r3_hfilt2<HAS_MASK>(wa, ma, col, k23, B);
         while ((int)yt.x == u) {
-          r3_emit2<HAS_MASK, FMT>(A, B, yt, out, plane_bytes, lut);
+          r3_emit2<HAS_MASK, FMT>(A, B, yt, out, plane_bytes, lut, k23);
           ya += kR3YtabEntry2;
           yt = r3_lds128(ya);
         }
@@ -635,7 +644,7 @@ __device__ __forceinline__ void r3_consumer8(const Roi3Params& p, uint32_t sb, i
           uint32_t v4[3];
 #pragma unroll
           for (int j = 0; j < 3; ++j) v4[j] = vpass(j);
-          r3_finish<HAS_MASK, FMT>(v4, m4, 0u, off, q, plane_bytes, lut);
+          r3_finish<HAS_MASK, FMT>(v4, m4, 0u, off, q, plane_bytes, lut, 0x4B000000u);
           ya += kR3YtabEntry8;
           yt = r3_lds128(ya);
         }
