@@ -329,14 +329,17 @@ __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, 
       asm("lop3.b32 %0, %1, 0x3FC, %2, 0xEA;" : "=r"(vb) : "r"(v4[c]), "r"(k23));
       o[c] = __float_as_uint(fmaf(__uint_as_float(vb), mr, cc));
     }
-  } else if (HAS_MASK && __any_sync(0xFFFFFFFFu, m4 - (base4 + 4u) < 1016u)) {
-    // fp32 output, a partially masked pixel in the warp: the exact quotient normalise_u8(v, m) for every lane, on
-    // X = 16 v m (each step of normalise_u8 scales by an exact power of two: bit-identical, no shifts)
+  } else if (HAS_MASK) {
+    // fp32 output (the reference's tensor) with a mask: the quotient must be exact in fp32.  normalise_u8(v, m) for every
+    // pixel, on X = (4v)(4m) = 16 v m (each step of normalise_u8 scales by an exact power of two: bit-identical, no
+    // shifts): m = 0 gives 0, m = 255 the table value.  Branch-free like the bf16 path - the table look-up with its vote,
+    // select and bank conflicts only paid off for warps the mask edge does not cross, and those are not the ones a strip
+    // waits for.
     const uint32_t mm = m4 & 0x3FCu;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float x = (float)((v4[c] & 0x3FCu) * mm);
-      const float r16 = (1.0f / 65025.0f) * 0.0625f;
+      constexpr float r16 = (1.0f / 65025.0f) * 0.0625f;
       const float qq = x * r16;
       o[c] = __float_as_uint(fmaf(fmaf(-qq, 16.0f * 65025.0f, x), r16, qq));
     }
@@ -351,7 +354,6 @@ __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, 
         asm("lop3.b32 %0, %1, 0x3FC, %2, 0xEA;" : "=r"(xb) : "r"(v4[c]), "r"(k23));
         o[c] = __float_as_uint(fmaf(__uint_as_float(xb), 1.0f / 1020.0f, -8388608.0f * (1.0f / 1020.0f)));
       }
-      if (FMT == 0 && HAS_MASK) o[c] = off ? 0u : o[c];
     }
   }
   if (FMT == 0) {
