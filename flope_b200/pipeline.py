@@ -4,7 +4,7 @@ Two modes.  serial_backbones=True (what bench.py uses): a step is split into a S
 ingest into the engine's stem input - small CTAs that fit on an SM beside a persistent conv CTA) and a RUN part
 (backbone + head).  The run parts of consecutive steps are chained by events, so two backbones never compete for the
 SMs and every engine keeps its fastest schedule (layer1..layer4 as one launch); only the staging of step i+1 overlaps
-step i.  Measured at 256 crops: ROI staging 905 -> 885 us per step, float32 ingest 885 -> 880 (tools/ab_staged.py) - the
+step i.  Measured at 256 crops: ROI staging 905 -> 885 us per step, float32 ingest 885 -> 880 (round-1 A/B runs, profiles/r1_notes.md) - the
 staging CTAs mostly run in the gaps between conv kernels rather than beside them, also with 128-thread blocks, a
 high-priority run stream and the conv kernels' shared-memory carve-out.  serial_backbones=False: fully independent steps, engines fall back to one launch per layer (see below).
 
