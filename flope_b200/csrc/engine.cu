@@ -909,7 +909,7 @@ int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W
       const int key = (lanczos ? 4 : 0) | (has_mask ? 2 : 0) | (out_fmt == FLOPE_OUT_ENGINE ? 1 : 0);
       cudaError_t ce;
       // up to 224 columns per item: 256 threads, five CTAs per SM (<= 48 registers); wider items: 288 threads
-#define ROI3_CASE(K, T, M, F) case K: ce = block <= 256 ? roi3_launch<T, M, F, 256, (T == 2 ? 5 : 3)>(q, e->num_sms, e->roi_ctas_per_sm, block, smem, st) \
+#define ROI3_CASE(K, T, M, F) case K: ce = block <= 256 ? roi3_launch<T, M, F, 256, (T == 2 ? 4 : 3)>(q, e->num_sms, e->roi_ctas_per_sm, block, smem, st) \
                                                        : roi3_launch<T, M, F, 288, (T == 2 ? 4 : 3)>(q, e->num_sms, e->roi_ctas_per_sm, block, smem, st); break;
       switch (key) {
         ROI3_CASE(0, 2, false, 0) ROI3_CASE(1, 2, false, 1) ROI3_CASE(2, 2, true, 0) ROI3_CASE(3, 2, true, 1)
