@@ -227,7 +227,20 @@ __global__ void __launch_bounds__(256) roi_crop_kernel(const __grid_constant__ R
   const int y_begin = blockIdx.y * p.rows_per_strip;
   const int y_end = min(S, y_begin + p.rows_per_strip);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (sw <= 0 || sh <= 0) return;                 // the host rejects empty boxes; never dereference one
+  if (sw <= 0 || sh <= 0) {                       // empty box (the Python layer rejects these): the crop is defined as zeros
+    if (x < S)
+      for (int y = y_begin; y < y_end; ++y) {
+        if (p.out_fmt == 0) {
+          float* o = reinterpret_cast<float*>(p.out) + ((long long)crop * 3 * S + y) * S + x;
+          o[0] = 0.f; o[(long long)S * S] = 0.f; o[2LL * S * S] = 0.f;
+        } else {
+          const long long pos = p.g.base + geom_pos(p.g, crop, y >> 1, x >> 1);
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)(y & 1) * p.g.plane + pos) * 8 + (x & 1) * 4;
+          *reinterpret_cast<uint2*>(dst) = make_uint2(0u, 0u);
+        }
+      }
+    return;
+  }
 
   const double scale_x = axis_scale(sw, S);
   const double scale_y = axis_scale(sh, S);

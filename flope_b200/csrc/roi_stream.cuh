@@ -165,11 +165,29 @@ __device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, in
     const int32_t* bx = p.boxes + (size_t)crop * 5;
     const int frame = __ldg(bx), xmin = __ldg(bx + 1), ymin = __ldg(bx + 2);
     const int sw = __ldg(bx + 3) - xmin, sh = __ldg(bx + 4) - ymin;
-    if (sw <= 0 || sh <= 0) continue;            // empty box: nothing to write (the host rejects these)
     const int S = p.S;
     const int y_begin = strip * p.rows_per_item, y_end = imin(S, y_begin + p.rows_per_item);
     const int x_begin = cb * p.cols_per_item, x_end = x_begin + p.cols_per_item;
     const int n_out = y_end - y_begin;
+    if (sw <= 0 || sh <= 0) {
+      // Empty box (the reference's cv2.resize raises; the Python layer rejects it): the crop is defined as zeros, so that
+      // its slot never keeps a previous batch's pixels.  A "zero item": the output row offsets only, no source rows.
+      const uint32_t zt = sb + kR3Ytab + r3_ytab_slot(TAPS) * b;
+      for (int i = lane; i < n_out; i += 32) {
+        const int y = y_begin + i;
+        const uint32_t ooff = p.out_fmt == 0 ? (uint32_t)y * (uint32_t)S * 4u
+                                             : (uint32_t)(y >> 1) * (uint32_t)p.g.Wp * 16u + ((y & 1) ? (uint32_t)(p.g.plane * 16) : 0u);
+        r3_sts32(zt + 4 * i, ooff);
+      }
+      if (lane == 0) {
+        r3_sts32(hdr + 4 * R3H_CROP, (uint32_t)crop); r3_sts32(hdr + 4 * R3H_NROWS, (uint32_t)n_out);
+        r3_sts32(hdr + 4 * R3H_XBEGIN, (uint32_t)x_begin); r3_sts32(hdr + 4 * R3H_VALID, 2u);
+      }
+      __syncwarp();
+      if (lane == 0) r3_bar_arrive(sb + kR3ItemFull + 8 * b);
+      ++it;
+      continue;
+    }
     const double scale_y = axis_scale(sh, S), scale_x = axis_scale(sw, S);
     float f;
     const int u_first = src_coord(y_begin, scale_y, f) - LO;
@@ -454,6 +472,23 @@ __device__ __forceinline__ void r3_consumer2(const Roi3Params& p, uint32_t sb, i
     const uint32_t hdr = sb + kR3Hdr + 64 * b;
     const U32x4 h0 = r3_lds128(hdr), h1 = r3_lds128(hdr + 16);
     if (h0.x == 0u) return;
+    if (h0.x == 2u) {                          // zero item (empty box): write zeros to the item's rows of this column
+      uint8_t* zo = out0 + (int)h0.y * crop_bytes + (int)h1.z * col_bytes;
+      const uint32_t zt = sb + kR3Ytab + r3_ytab_slot(TAPS) * b;
+      for (int i = 0; i < (int)h0.w; ++i) {
+        uint8_t* q = zo + r3_lds32(zt + 4 * i);
+        if (FMT == 0) {
+          *reinterpret_cast<uint32_t*>(q) = 0u;
+          *reinterpret_cast<uint32_t*>(q + plane_bytes) = 0u;
+          *reinterpret_cast<uint32_t*>(q + 2 * (size_t)plane_bytes) = 0u;
+        } else {
+          *reinterpret_cast<uint2*>(q) = make_uint2(0u, 0u);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) r3_bar_arrive(sb + kR3ItemEmpty + 8 * b);
+      continue;
+    }
     int u = (int)h0.z, rows_left = (int)h0.w;
     const int K = (int)h1.x;
     const uint32_t pitch = h1.y;
@@ -587,6 +622,23 @@ __device__ __forceinline__ void r3_consumer8(const Roi3Params& p, uint32_t sb, i
     const uint32_t hdr = sb + kR3Hdr + 64 * b;
     const U32x4 h0 = r3_lds128(hdr), h1 = r3_lds128(hdr + 16), h2 = r3_lds128(hdr + 32);
     if (h0.x == 0u) return;
+    if (h0.x == 2u) {                          // zero item (empty box): write zeros to the item's rows of this column
+      uint8_t* zo = out0 + (int)h0.y * crop_bytes + (int)h1.z * col_bytes;
+      const uint32_t zt = sb + kR3Ytab + r3_ytab_slot(TAPS) * b;
+      for (int i = 0; i < (int)h0.w; ++i) {
+        uint8_t* q = zo + r3_lds32(zt + 4 * i);
+        if (FMT == 0) {
+          *reinterpret_cast<uint32_t*>(q) = 0u;
+          *reinterpret_cast<uint32_t*>(q + plane_bytes) = 0u;
+          *reinterpret_cast<uint32_t*>(q + 2 * (size_t)plane_bytes) = 0u;
+        } else {
+          *reinterpret_cast<uint2*>(q) = make_uint2(0u, 0u);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) r3_bar_arrive(sb + kR3ItemEmpty + 8 * b);
+      continue;
+    }
     int u = (int)h0.z, rows_left = (int)h0.w;
     const int K = (int)h1.x;
     const uint32_t pitch = h1.y, rgb0 = h1.w, msk0 = h2.x;

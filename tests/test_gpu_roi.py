@@ -250,3 +250,37 @@ def test_engine_format_masked_normalise_exhaustive(cuda_lib, interp):
         assert not x0[3::4].any()                                              # the pad lane of every pixel stays zero
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("interp,size", [(R.BILINEAR, 224), (R.LANCZOS4, 512)])
+@pytest.mark.parametrize("stream", [1, 0])
+def test_empty_boxes_give_zero_crops_and_do_not_disturb_the_others(cuda_lib, interp, size, stream):
+    """Boxes that are already on the device cannot be range-checked by the host.  The reference's cv2.resize raises on an
+    empty slice; the kernels define such a crop as zeros (its output slot must never keep a previous batch's pixels) and
+    the neighbouring crops stay bit-exact - in the streaming kernels and in the generic one."""
+    rng = np.random.default_rng(77)
+    frame, mask = _frame(rng)
+    boxes = np.array([[100, 50, 137, 87], [60, 60, 60, 90], [10, 10, 234, 234], [70, 80, 40, 50], [200, 100, 301, 201]], np.int32)
+    b5 = torch.from_numpy(np.concatenate([np.zeros((5, 1), np.int32), boxes], 1)).cuda()       # device boxes: no host check
+    e = cuda_lib.Engine(0, max_batch=8, crop_hw=size)
+    try:
+        e.debug_set("roi_stream", stream)
+        out = torch.full((5, 3, size, size), 7.0, device="cuda")
+        fr, mk = torch.from_numpy(frame).cuda()[None], torch.from_numpy(mask).cuda()[None]
+        e.roi_crop(fr, mk, b5, size, interp, out=out)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert not got[1].any() and not got[3].any()
+        want = R.crop_batch_reference(frame, mask, boxes[[0, 2, 4]], size=size, interp=interp)
+        assert np.array_equal(got[[0, 2, 4]], want)
+        if size == 224:
+            # engine format: run a valid batch first, then the batch with empty boxes - their stem-input slots must be zero
+            valid = b5.clone(); valid[1, 1:] = torch.tensor([0, 0, 50, 50]); valid[3, 1:] = torch.tensor([5, 5, 90, 90])
+            e.roi_crop(fr, mk, valid, size, interp, out_fmt=cuda_lib.OUT_ENGINE)
+            e.roi_crop(fr, mk, b5, size, interp, out_fmt=cuda_lib.OUT_ENGINE)
+            buf, chw = e.debug_activation("x0", 5)
+            torch.cuda.synchronize()
+            x0 = buf.cpu().numpy().reshape(5, -1)
+            assert not x0[1].any() and not x0[3].any() and x0[0].any() and x0[2].any()
+    finally:
+        e.close()
