@@ -229,7 +229,7 @@ struct flope_engine {
   int roi_stream = 1;                            // streaming ROI kernels (roi3_kernel, roi_stream.cuh): the production path
   int roi_item_rows = 56;                        // output rows per work item of the streaming bilinear kernel
   int roi_item_rows8 = 128;                       // same for the streaming Lanczos4 kernel
-  int roi_stage_kb = 10;                         // bytes per ring stage of the streaming kernels
+  int roi_stage_kb = 14;                         // bytes per ring stage of the streaming kernels
   int roi_stages = 3;                            // ring depth
   int roi_ctas_per_sm = 0;                       // 0 = as many as fit
   bool chain_coop = false;                       // launch chains cooperatively (gang-scheduled): needed when several engines share a device
