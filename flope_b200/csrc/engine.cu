@@ -240,6 +240,9 @@ struct flope_engine {
   int chain_dynamic = 0;                     // chains claim work items from an atomic counter (safe under partial residency)
   bool use_chain = true;                         // one persistent launch per ResNet stage (four convs) with per-tile completion flags
   std::vector<std::vector<int>> chains;          // layer indices of each stage
+  uint32_t* d_roi_tab = nullptr;                 // Lanczos4 axis tables of the current ROI launch (grown on demand)
+  size_t roi_tab_words = 0;
+  int roi_axis_tab = 1;                          // Lanczos4: coefficient tables from a pre-kernel (0 = the producer warps compute them)
   unsigned int* d_roi_sched = nullptr;           // work counter of the streaming ROI kernels (self-resetting)
   int roi_dynamic = 1;                           // streaming ROI kernels claim items from the counter (0 = static round-robin)
   uint32_t* d_flags = nullptr;                   // completion counters of all chains, zeroed at the start of every forward
@@ -901,6 +904,20 @@ int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W
     q.stage_bytes = (std::max(e->roi_stage_kb * 1024, (lanczos ? 1 : 2) * max_pitch) + 127) & ~127;
     q.n_stages = std::max(2, std::min(kR3MaxStages, e->roi_stages));
     q.sched = e->roi_dynamic ? e->d_roi_sched : nullptr;
+    if (lanczos && e->roi_axis_tab) {
+      // the Lanczos4 coefficient tables of every crop and axis, computed by the whole GPU instead of the producer warps
+      const size_t words = (size_t)n * 2 * S * 8;
+      if (words > e->roi_tab_words) {
+        if (e->d_roi_tab) CUDA_TRY(cudaFree(e->d_roi_tab));          // (synchronises: nothing in flight uses the old table)
+        e->d_roi_tab = nullptr; e->roi_tab_words = 0;
+        CUDA_TRY(cudaMalloc(&e->d_roi_tab, words * sizeof(uint32_t)));
+        e->roi_tab_words = words;
+      }
+      const long long total = 2LL * n * S;
+      roi3_axis_tables_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_boxes, n, S, e->d_roi_tab);
+      ++e->launches;
+      q.axis_tab = e->d_roi_tab;
+    }
     q.xtab_slot = cw * (lanczos ? kR3XtabEntry8 : kR3XtabEntry2);
     q.ring_off = (r3_xtab_off(lanczos ? 8 : 2) + 2 * q.xtab_slot + 127) & ~127;
     const size_t smem = (size_t)q.ring_off + (size_t)q.n_stages * q.stage_bytes + kR3RingTail;
@@ -1016,6 +1033,7 @@ void flope_engine_destroy(flope_engine* e) {
   cudaFree(e->stem_pool.d_w); cudaFree(e->stem_pool.d_bias);
   cudaFree(e->d_flags);
   cudaFree(e->d_roi_sched);
+  cudaFree(e->d_roi_tab);
   cudaFree(e->d_stamps);
   cudaFree(e->d_feat); cudaFree(e->d_wrot); cudaFree(e->d_brot); cudaFree(e->d_r9);
   delete e;
@@ -1388,6 +1406,7 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
     e->roi_stages = value;
     return FLOPE_OK;
   }
+  if (!std::strcmp(key, "roi_axis_tab")) { e->roi_axis_tab = value; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_dynamic")) { e->roi_dynamic = value; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_ctas_per_sm")) { e->roi_ctas_per_sm = value; return FLOPE_OK; }
   if (!std::strcmp(key, "chain_coop")) { e->chain_coop = value != 0; drop_graphs(e); return FLOPE_OK; }

@@ -55,6 +55,8 @@ struct Roi3Params {
   int n_stages;               // <= kR3MaxStages
   int xtab_slot;              // cols_per_item * bytes per horizontal table entry
   int ring_off;               // r3_xtab_off(TAPS) + 2 * xtab_slot, multiple of 128
+  const uint32_t* axis_tab;   // Lanczos4 only: [crop][axis: 0 = x, 1 = y][S] entries of 8 words {floor(src coord), c01, c23, c45, c67, 0, 0, 0},
+                              // built by roi3_axis_tables_kernel right before the launch (nullptr: the producer computes them)
   unsigned int* sched;        // {next item, CTAs done}: both zero at launch, reset by the last CTA (nullptr = static round-robin)
 };
 
@@ -140,6 +142,41 @@ __device__ __forceinline__ int r3_next_item(const Roi3Params& p, int item, int l
   unsigned int v = 0;
   if (lane == 0) v = atomicAdd(p.sched, 1u);
   return (int)gridDim.x + (int)__shfl_sync(0xFFFFFFFFu, v, 0);
+}
+
+// Lanczos4 coefficients of destination index d along one axis: from the per-launch table when there is one (the double
+// precision sin / cos / divisions of cv2's formula are ~1000 instructions per entry - far too much for ONE producer warp
+// that has to keep eight consumer warps fed), else computed in place.
+__device__ __forceinline__ void r3_lanczos_entry(const Roi3Params& p, int crop, int axis, int d, double scale, int& s_out, short (&ic)[8]) {
+  if (p.axis_tab) {
+    const uint4* e = reinterpret_cast<const uint4*>(p.axis_tab + (((size_t)crop * 2 + axis) * p.S + d) * 8);
+    const uint4 a = __ldg(e);
+    const uint32_t c67 = __ldg(reinterpret_cast<const uint32_t*>(e + 1));
+    s_out = (int)a.x;
+    ic[0] = (short)(a.y & 0xFFFFu); ic[1] = (short)(a.y >> 16); ic[2] = (short)(a.z & 0xFFFFu); ic[3] = (short)(a.z >> 16);
+    ic[4] = (short)(a.w & 0xFFFFu); ic[5] = (short)(a.w >> 16); ic[6] = (short)(c67 & 0xFFFFu); ic[7] = (short)(c67 >> 16);
+  } else {
+    lanczos4_coefs(d, scale, s_out, ic);
+  }
+}
+__global__ void __launch_bounds__(256) roi3_axis_tables_kernel(const int32_t* boxes, int n, int S, uint32_t* tab) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2LL * n * S) return;
+  const int d = (int)(i % S), axis = (int)((i / S) & 1), crop = (int)(i / (2LL * S));
+  const int32_t* bx = boxes + (size_t)crop * 5;
+  const int src = axis ? bx[4] - bx[2] : bx[3] - bx[1];
+  uint4 a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(0u, 0u, 0u, 0u);
+  if (src > 0) {
+    short ic[8]; int s;
+    lanczos4_coefs(d, axis_scale(src, S), s, ic);
+    a.x = (uint32_t)s;
+    a.y = (uint32_t)(uint16_t)ic[0] | ((uint32_t)(uint16_t)ic[1] << 16);
+    a.z = (uint32_t)(uint16_t)ic[2] | ((uint32_t)(uint16_t)ic[3] << 16);
+    a.w = (uint32_t)(uint16_t)ic[4] | ((uint32_t)(uint16_t)ic[5] << 16);
+    b.x = (uint32_t)(uint16_t)ic[6] | ((uint32_t)(uint16_t)ic[7] << 16);
+  }
+  uint4* e = reinterpret_cast<uint4*>(tab + (size_t)i * 8);
+  e[0] = a; e[1] = b;
 }
 
 template <int TAPS, bool HAS_MASK>
@@ -252,7 +289,7 @@ __device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, in
         if (i == n_out) e0.x = 0x7FFFFFFFu;
         else {
           short ic[8]; int sy;
-          lanczos4_coefs(y, scale_y, sy, ic);
+          r3_lanczos_entry(p, crop, 1, y, scale_y, sy, ic);
           e0.x = (uint32_t)(sy + 4);
           uint32_t cf[8];
           // ring slot k holds the source row u with (u & 7) == k; the window is u = sy - 3 + j
@@ -285,7 +322,7 @@ __device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, in
         r3_sts128(xa, e);
       } else {
         short ic[8]; int sx;
-        lanczos4_coefs(x_begin + i, scale_x, sx, ic);
+        r3_lanczos_entry(p, crop, 0, x_begin + i, scale_x, sx, ic);
         const int rel = sx - 3 - xc0;                  // first tap relative to the first staged pixel (>= -4)
         const uint32_t bo = (uint32_t)((int)rgb0 + 3 * rel), bm = (uint32_t)((int)msk0o + rel);
         U32x4 e0, e1;
