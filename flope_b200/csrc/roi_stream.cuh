@@ -17,15 +17,18 @@
 //                 filter of the row into registers (aligned 32-bit words, funnel shift, byte permute, DP2A), then
 //                 every output row this source row completes is emitted (vertical filter, mask, normalise, store).
 //                 Source rows are filtered once per strip and column, raw rows are dead as soon as they are filtered,
-//                 so a stage is handed back to the producer after a few rows: the ring is small (3 x ~10 KB), several
-//                 CTAs fit an SM and loads run ahead of compute.
+//                 so a stage is handed back to the producer after a few rows: the ring is small (3 x 14 KB), four
+//                 CTAs fit an SM and loads run ahead of compute.  The warps of a CTA move through the ring together:
+//                 a strip costs what its busiest warp costs, so the per-pixel work is kept branch-free and identical
+//                 for every warp (see r3_finish) instead of offering shortcuts to warps with masked-out pixels.
 //
 // Bilinear: the register window is two rows (the loop is unrolled over a row pair, no data moves).  The vertical
 // pass - two separately truncated products in cv2 - runs on the FMA pipe with round-toward-minus-infinity FMAs
-// (r3_emit2), not as 32x32 high multiplies.
+// (r3_emit2), not as 32x32 high multiplies; the masked normalise is two more FMAs per channel on the same bit patterns.
 // Lanczos4: the register window is a ring of eight rows indexed by (source row & 7); the table rotates the
 // coefficients instead of the data.  The replicated border left / right of the crop is written into the padding of
-// the staged rows by the warps whose columns reach it (a warp patches for itself, so no CTA-wide barrier).
+// the staged rows by the warps whose columns reach it (a warp patches for itself, so no CTA-wide barrier).  The
+// coefficient tables (cv2's double-precision formula) come from a pre-kernel, roi3_axis_tables_kernel.
 //
 // Requirements checked by the host (engine.cu: run_roi): W % 16 == 0 (the 16-byte phase of a row segment is the
 // same for every row of a crop), cols_per_item a multiple of 32, rows fit a stage.  Anything else takes roi_crop_kernel.
