@@ -70,6 +70,8 @@ constexpr int kR3Full = 0;                     // mbarrier per stage: rows have 
 constexpr int kR3Empty = 64;                   // mbarrier per stage: every consumer warp is done with the rows
 constexpr int kR3ItemFull = 128;               // mbarrier per item slot: header + tables written
 constexpr int kR3ItemEmpty = 144;              // mbarrier per item slot: every consumer warp is done with them
+constexpr int kR3Konst = 176;                  // 4 words of fp32 constants the bf16 consumers keep in registers (read once from here:
+                                               // an immediate would be re-materialised inside the loop by ptxas)
 constexpr int kR3Hdr = 192;                    // 2 x 64 B
 constexpr int kR3Ytab = 320;                   // 2 x (kR3MaxItemRows + 1) entries
 constexpr int kR3YtabEntry2 = 16;              // linear : {u_top, float b0 * 2^-20, float b1 * 2^-20, output row offset}
@@ -364,9 +366,11 @@ __device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, in
 //   fmt 0: three fp32 words; unmasked values come from the 256-entry table in shared memory
 // fp32 output: the branch is warp-uniform (a vote) - a warp with a partially masked pixel (mask edge) takes the general
 // quotient for every lane, everything else takes the unmasked path and zeroes its masked-out lanes with a select.
+constexpr float kR3MaskedR = (1.0f / 65025.0f) * 0.0625f;     // fl(1/65025) / 16
+constexpr float kR3PlainR = 1.0f / 1020.0f;
 template <bool HAS_MASK, int FMT>
 __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, uint32_t base4, bool off, uint8_t* q,
-                                          uint32_t plane_bytes, uint32_t lut, uint32_t k23) {
+                                          uint32_t plane_bytes, uint32_t lut, uint32_t k23, float kn) {
   uint32_t o[3];
   if (FMT == 1 && HAS_MASK) {
     // bf16 output with a mask: ONE branch-free expression for every pixel, two instructions per channel.
@@ -376,10 +380,10 @@ __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, 
     // fp32 values themselves differ below bf16 resolution; tests/test_gpu_roi.py checks the device exhaustively), m = 0
     // gives exactly 0 and m = 255 the unmasked value: no vote, no select, and every warp of a strip does the same work
     // whether the mask edge crosses it or not.
-    constexpr float R = (1.0f / 65025.0f) * 0.0625f;
+    constexpr float R = kR3MaskedR;                    // == kn, which the caller holds in a register
     uint32_t mb;
     asm("lop3.b32 %0, %1, 0x3FC, %2, 0xEA;" : "=r"(mb) : "r"(m4), "r"(k23));
-    const float mr = fmaf(__uint_as_float(mb), R, -8388608.0f * R);
+    const float mr = fmaf(__uint_as_float(mb), kn, -8388608.0f * R);
     const float cc = mr * -8388608.0f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -410,7 +414,7 @@ __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, 
         // (float)(4v) without a conversion: the integer sits in the mantissa of 2^23 + 4v
         uint32_t xb;
         asm("lop3.b32 %0, %1, 0x3FC, %2, 0xEA;" : "=r"(xb) : "r"(v4[c]), "r"(k23));
-        o[c] = __float_as_uint(fmaf(__uint_as_float(xb), 1.0f / 1020.0f, -8388608.0f * (1.0f / 1020.0f)));
+        o[c] = __float_as_uint(fmaf(__uint_as_float(xb), kn, -8388608.0f * kR3PlainR));          // kn == kR3PlainR
       }
     }
   }
@@ -470,11 +474,15 @@ __device__ __forceinline__ float r3_fma_rm(float a, float b, float c) {
 }
 template <bool HAS_MASK, int FMT>
 __device__ __forceinline__ void r3_emit2(const uint32_t (&lo)[HAS_MASK ? 4 : 3], const uint32_t (&up)[HAS_MASK ? 4 : 3],
-                                         const U32x4& yt, uint8_t* out, uint32_t plane_bytes, uint32_t lut, uint32_t k23) {
+                                         const U32x4& yt, uint8_t* out, uint32_t plane_bytes, uint32_t lut, uint32_t k23, float kn) {
   constexpr int NCH = HAS_MASK ? 4 : 3;
   constexpr uint32_t kBase = 0x4B400000u;    // 1.5 * 2^23
   const float b0 = __uint_as_float(yt.y), b1 = __uint_as_float(yt.z);
-  const float m0 = fmaf(b0 + b1, -8388608.0f, 12582914.0f);
+  // b0 + b1 == 2048 for every destination row of every source size up to 16384 and every S this kernel is launched
+  // with (S % 32 == 0, S <= 512): the vertical fraction is within 2^-27 of a rational with denominator 2S, which is never
+  // closer than 1/lcm(2S, 4096) >= 2^-22 to a rounding tie of 2048 * frac, so the two roundings are complementary;
+  // tests/test_roi_coefs.py checks all of them.  Hence M0 is a constant.
+  constexpr float m0 = 12582914.0f - 8.0f * 2048.0f;
   uint32_t m4 = kBase + 1020u;
   if (HAS_MASK) m4 = __float_as_uint(r3_fma_rm(b1, __uint_as_float(up[NCH - 1]), r3_fma_rm(b0, __uint_as_float(lo[NCH - 1]), m0)));
   const bool off = HAS_MASK && m4 < kBase + 4u;      // masked out: exactly zero whatever the image holds
@@ -483,7 +491,7 @@ __device__ __forceinline__ void r3_emit2(const uint32_t (&lo)[HAS_MASK ? 4 : 3],
   uint32_t v4[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) v4[j] = __float_as_uint(r3_fma_rm(b1, __uint_as_float(up[j]), r3_fma_rm(b0, __uint_as_float(lo[j]), m0)));
-  r3_finish<HAS_MASK, FMT>(v4, m4, kBase, off, out + yt.w, plane_bytes, lut, k23);
+  r3_finish<HAS_MASK, FMT>(v4, m4, kBase, off, out + yt.w, plane_bytes, lut, k23, kn);
 }
 
 template <bool HAS_MASK, int FMT>
@@ -504,8 +512,8 @@ __device__ __forceinline__ void r3_consumer2(const Roi3Params& p, uint32_t sb, i
   }
   const long long crop_bytes = FMT == 0 ? 3LL * S * S * 4 : (long long)p.g.Hp * p.g.Wp * 16;
   const int col_bytes = FMT == 0 ? 4 : 8;
-  uint32_t k23;                              // the bit pattern of 2^23, opaque to ptxas so that it stays in a register
-  asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(k23));
+  const uint32_t k23 = r3_lds32(sb + kR3Konst + 8);   // the bit pattern of 2^23; read from shared memory so that it stays in a register
+  const float kn = __uint_as_float(r3_lds32(sb + kR3Konst + (HAS_MASK ? 0 : 4)));   // the normalise factor of r3_finish (bf16 output)
   for (int it = 0;; ++it) {
     const int b = it & 1;
     r3_bar_wait(sb + kR3ItemFull + 8 * b, ((uint32_t)it >> 1) & 1u);
@@ -553,14 +561,14 @@ __device__ __forceinline__ void r3_consumer2(const Roi3Params& p, uint32_t sb, i
       while (u != u_end) {
         r3_hfilt2<HAS_MASK>(wa, ma, col, k23, A);
         while ((int)yt.x == u) {             // output rows whose upper source row is u
-          r3_emit2<HAS_MASK, FMT>(B, A, yt, out, plane_bytes, lut, k23);
+          r3_emit2<HAS_MASK, FMT>(B, A, yt, out, plane_bytes, lut, k23, kn);
           ya += kR3YtabEntry2;
           yt = r3_lds128(ya);
         }
         ++u; wa += pitch; ma += pitch;
         r3_hfilt2<HAS_MASK>(wa, ma, col, k23, B);
         while ((int)yt.x == u) {
-          r3_emit2<HAS_MASK, FMT>(A, B, yt, out, plane_bytes, lut, k23);
+          r3_emit2<HAS_MASK, FMT>(A, B, yt, out, plane_bytes, lut, k23, kn);
           ya += kR3YtabEntry2;
           yt = r3_lds128(ya);
         }
@@ -738,7 +746,7 @@ __device__ __forceinline__ void r3_consumer8(const Roi3Params& p, uint32_t sb, i
           uint32_t v4[3];
 #pragma unroll
           for (int j = 0; j < 3; ++j) v4[j] = vpass(j);
-          r3_finish<HAS_MASK, FMT>(v4, m4, 0u, off, q, plane_bytes, lut, 0x4B000000u);
+          r3_finish<HAS_MASK, FMT>(v4, m4, 0u, off, q, plane_bytes, lut, 0x4B000000u, HAS_MASK ? kR3MaskedR : kR3PlainR);
           ya += kR3YtabEntry8;
           yt = r3_lds128(ya);
         }
@@ -766,6 +774,9 @@ __global__ void __launch_bounds__(MAXT, MINB) roi3_kernel(const __grid_constant_
     if (sb & 1023u) __trap();
     for (int s = 0; s < p.n_stages; ++s) { r3_bar_init(sb + kR3Full + 8 * s, 1u); r3_bar_init(sb + kR3Empty + 8 * s, (uint32_t)n_cons); }
     for (int b = 0; b < 2; ++b) { r3_bar_init(sb + kR3ItemFull + 8 * b, 1u); r3_bar_init(sb + kR3ItemEmpty + 8 * b, (uint32_t)n_cons); }
+    r3_sts32(sb + kR3Konst, f32_bits(kR3MaskedR));
+    r3_sts32(sb + kR3Konst + 4, f32_bits(kR3PlainR));
+    r3_sts32(sb + kR3Konst + 8, 0x4B000000u);
     mbar_fence_init();
   }
   if (FMT == 0) for (int i = t; i < 256; i += blockDim.x) r3_sts32(sb + r3_lut_off(TAPS) + 4 * i, f32_bits(normalise_u8(i, 255)));
