@@ -368,7 +368,8 @@ __device__ __forceinline__ void r3_producer(const Roi3Params& p, uint32_t sb, in
 // quotient for every lane, everything else takes the unmasked path and zeroes its masked-out lanes with a select.
 constexpr float kR3MaskedR = (1.0f / 65025.0f) * 0.0625f;     // fl(1/65025) / 16
 constexpr float kR3PlainR = 1.0f / 1020.0f;
-template <bool HAS_MASK, int FMT>
+// PLAIN (fp32 output with a mask only): v4 / m4 hold the plain cv2 result 0..255 instead.
+template <bool HAS_MASK, int FMT, bool PLAIN = false>
 __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, uint32_t base4, bool off, uint8_t* q,
                                           uint32_t plane_bytes, uint32_t lut, uint32_t k23, float kn) {
   uint32_t o[3];
@@ -397,13 +398,13 @@ __device__ __forceinline__ void r3_finish(const uint32_t (&v4)[3], uint32_t m4, 
     // shifts): m = 0 gives 0, m = 255 the table value.  Branch-free like the bf16 path - the table look-up with its vote,
     // select and bank conflicts only paid off for warps the mask edge does not cross, and those are not the ones a strip
     // waits for.
-    const uint32_t mm = m4 & 0x3FCu;
+    const uint32_t mm = PLAIN ? m4 : (m4 & 0x3FCu);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float x = (float)((v4[c] & 0x3FCu) * mm);
-      constexpr float r16 = (1.0f / 65025.0f) * 0.0625f;
+      const float x = (float)((PLAIN ? v4[c] : (v4[c] & 0x3FCu)) * mm);
+      constexpr float r16 = PLAIN ? 1.0f / 65025.0f : (1.0f / 65025.0f) * 0.0625f;
       const float qq = x * r16;
-      o[c] = __float_as_uint(fmaf(fmaf(-qq, 16.0f * 65025.0f, x), r16, qq));
+      o[c] = __float_as_uint(fmaf(fmaf(-qq, PLAIN ? 65025.0f : 16.0f * 65025.0f, x), r16, qq));
     }
   } else {
 #pragma unroll
@@ -734,11 +735,13 @@ __device__ __forceinline__ void r3_consumer8(const Roi3Params& p, uint32_t sb, i
           const U32x4 ca = r3_lds128(ya + 16), cb = r3_lds128(ya + 32);
           const int cf[8] = {(int)ca.x, (int)ca.y, (int)ca.z, (int)ca.w, (int)cb.x, (int)cb.y, (int)cb.z, (int)cb.w};
           // 4 x the cv2 result, clamped: ((acc + 2^21) >> 22 clamped to 0..255) * 4 == ((acc + 2^21) >> 20 clamped to 0..1023) & 0x3FC
+          // (what the table look-up and the bf16 bit patterns index with); the masked fp32 quotient takes the plain 0..255
+          constexpr bool PLAIN = HAS_MASK && FMT == 0;
           auto vpass = [&](int j) {
             int acc = 1 << 21;
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc += R[i][j] * cf[i];
-            return (uint32_t)__vimin_s32_relu(acc >> 20, 1023);        // max(min(x, 1023), 0) in one VIMNMX.RELU
+            return (uint32_t)__vimin_s32_relu(acc >> (PLAIN ? 22 : 20), PLAIN ? 255 : 1023);   // max(min(x, hi), 0) in one VIMNMX.RELU
           };
           const uint32_t m4 = HAS_MASK ? vpass(NCH - 1) : 1020u;
           const bool off = HAS_MASK && m4 < 4u;
@@ -746,7 +749,7 @@ __device__ __forceinline__ void r3_consumer8(const Roi3Params& p, uint32_t sb, i
           uint32_t v4[3];
 #pragma unroll
           for (int j = 0; j < 3; ++j) v4[j] = vpass(j);
-          r3_finish<HAS_MASK, FMT>(v4, m4, 0u, off, q, plane_bytes, lut, 0x4B000000u, HAS_MASK ? kR3MaskedR : kR3PlainR);
+          r3_finish<HAS_MASK, FMT, PLAIN>(v4, m4, 0u, off, q, plane_bytes, lut, 0x4B000000u, HAS_MASK ? kR3MaskedR : kR3PlainR);
           ya += kR3YtabEntry8;
           yt = r3_lds128(ya);
         }
