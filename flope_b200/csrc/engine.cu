@@ -226,6 +226,8 @@ struct flope_engine {
   std::map<std::string, int> act_names;          // debug name -> buffer index
   std::vector<ConvLayer> layers;
   ConvLayer stem_pool;                           // stem conv with the max-pool fused into its epilogue
+  int roi_item_floor = 14;
+  int roi_item_auto = 1;                         // smaller items for launches that would not fill the persistent grid
   int roi_stream = 1;                            // streaming ROI kernels (roi3_kernel, roi_stream.cuh): the production path
   int roi_item_rows = 56;                        // output rows per work item of the streaming bilinear kernel
   int roi_item_rows8 = 128;                       // same for the streaming Lanczos4 kernel
@@ -893,9 +895,17 @@ int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W
     Roi3Params q{};
     q.frames = d_frames; q.frame_stride = frame_stride; q.masks = d_masks; q.mask_stride = (long long)H * W; q.W = W;
     q.boxes = d_boxes; q.n = n; q.S = S; q.out_fmt = out_fmt; q.out = rp.out; q.g = rp.g;
-    q.rows_per_item = std::max(1, std::min(std::min(kR3MaxItemRows, S), lanczos ? e->roi_item_rows8 : e->roi_item_rows));
     q.cols_per_item = cw;
     q.col_blocks = S / cw;
+    q.rows_per_item = std::max(1, std::min(std::min(kR3MaxItemRows, S), lanczos ? e->roi_item_rows8 : e->roi_item_rows));
+    if (e->roi_item_auto) {
+      // small launches (a streamed frame with a few flowers, one 256-crop step): halve the items until every resident CTA
+      // has about three to claim - an item re-reads 1 (Lanczos4: 7) source rows of its neighbour, hence the floors
+      const long long want = 3LL * e->num_sms * (lanczos ? 3 : 4);
+      const int floor_rows = lanczos ? 32 : e->roi_item_floor;
+      while (q.rows_per_item / 2 >= floor_rows && (long long)n * ((S + q.rows_per_item - 1) / q.rows_per_item) * q.col_blocks < want)
+        q.rows_per_item /= 2;
+    }
     q.items_per_crop = (S + q.rows_per_item - 1) / q.rows_per_item * q.col_blocks;
     const long long n_items = (long long)n * q.items_per_crop;
     q.n_items = (int)n_items;
@@ -925,7 +935,7 @@ int run_roi(flope_engine* e, const uint8_t* d_frames, int n_frames, int H, int W
       const int block = cw + 32;
       const int key = (lanczos ? 4 : 0) | (has_mask ? 2 : 0) | (out_fmt == FLOPE_OUT_ENGINE ? 1 : 0);
       cudaError_t ce;
-      // up to 224 columns per item: 256 threads, five CTAs per SM (<= 48 registers); wider items: 288 threads
+      // up to 224 columns per item: 256 threads, four CTAs per SM (<= 64 registers; Lanczos4: three); wider items: 288 threads
 #define ROI3_CASE(K, T, M, F) case K: ce = block <= 256 ? roi3_launch<T, M, F, 256, (T == 2 ? 4 : 3)>(q, e->num_sms, e->roi_ctas_per_sm, block, smem, st) \
                                                        : roi3_launch<T, M, F, 288, (T == 2 ? 4 : 3)>(q, e->num_sms, e->roi_ctas_per_sm, block, smem, st); break;
       switch (key) {
@@ -1391,9 +1401,12 @@ int flope_debug_set(flope_engine* e, const char* key, int value) {
   if (!e || !key) return fail(FLOPE_EINVAL, "NULL argument");
   if (!std::strcmp(key, "use_graph")) { e->use_graph = value != 0; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_stream")) { e->roi_stream = value; return FLOPE_OK; }
+  if (!std::strcmp(key, "roi_item_auto")) { e->roi_item_auto = value; return FLOPE_OK; }
+  if (!std::strcmp(key, "roi_item_floor")) { e->roi_item_floor = std::max(1, value); return FLOPE_OK; }
   if (!std::strcmp(key, "roi_item_rows") || !std::strcmp(key, "roi_item_rows8")) {
     if (value < 1 || value > kR3MaxItemRows) return fail(FLOPE_EINVAL, "roi_item_rows must be in [1,128]");
     (key[13] ? e->roi_item_rows8 : e->roi_item_rows) = value;
+    e->roi_item_auto = 0;                       // an explicit size is taken as given
     return FLOPE_OK;
   }
   if (!std::strcmp(key, "roi_stage_kb")) {

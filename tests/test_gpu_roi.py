@@ -92,8 +92,9 @@ def _b5(boxes, frame=0):
 
 
 # (stream, item rows, stage KB, ring stages, CTAs per SM, dynamic claiming): the streaming kernels under several launch
-# geometries - tiny stages (one or two rows per stage), short and tall items, a single CTA per SM - and the generic kernel
-_ROI_MODES = [(1, 0, 0, 0, 0, 1), (1, 7, 1, 2, 1, 0), (1, 16, 4, 4, 0, 1), (1, 128, 16, 3, 2, 1), (0, 0, 0, 0, 0, 1)]
+# geometries - the default (items sized to the launch), the large-launch item size, tiny stages (one or two rows per
+# stage), short and tall items, a single CTA per SM - and the generic kernel
+_ROI_MODES = [(1, 0, 0, 0, 0, 1), (1, 56, 14, 3, 0, 1), (1, 7, 1, 2, 1, 0), (1, 16, 4, 4, 0, 1), (1, 128, 16, 3, 2, 1), (0, 0, 0, 0, 0, 1)]
 
 
 def _set_roi_mode(e, mode, lanczos):
