@@ -114,6 +114,7 @@ struct ConvParams {
 // input buffer, may also overwrite that buffer's tile t once they are done; every finished tile publishes itself in
 // `flags` (a counter per position tile: n_n_tiles x CTAs of a pair parts), consumers wait on the three counters.
 constexpr int kMaxChain = 4;
+constexpr int kMaxSplit = 4;
 struct ConvChain {
   ConvParams L[kMaxChain];
   int n_layers;
@@ -134,6 +135,16 @@ struct ConvChain {
   // life - it does not count while every warp of the SM is parked in a barrier wait.)  nullptr in production.
   unsigned long long* stamps;
   uint32_t* claims;            // [CTA pairs][kClaimRing] leader -> peer hand-over of the claimed items (pair kernels)
+  // Split-K (trunk_chain_kernel, latency tiles only; 0 or 1 = off).  A streamed frame with a handful of flowers leaves
+  // layer3 / layer4 with 28 / 16 tiles for 74 CTA pairs, each a serial chain of 144 / 288 MMAs: every (position, channel)
+  // tile becomes k_splits consecutive work items over disjoint K-group ranges.  Items 0 .. k_splits-2 store their raw
+  // fp32 accumulators in split_ws and count themselves in split_flags; the last one adds them to its own in index
+  // order (a fixed order: results do not depend on timing) and runs the usual epilogue.
+  int k_splits;
+  uint32_t* split_flags;       // [n_layers][n_work] partial counters, zeroed with the tile flags
+  float4* split_ws;            // [n_work][k_splits-1][2 ranks][N_TILE/4 column quads][128 rows] of this stage
+  unsigned char split_group[kMaxChain][kMaxSplit + 1];    // K-group range of every split, per layer
+  unsigned short split_tap[kMaxChain][kMaxSplit + 1];     // weight tiles (taps) ahead of every split
 };
 constexpr int kStampWords = 8;
 constexpr int kClaimQ = 4;     // claimed items a CTA may hold ahead of its epilogue

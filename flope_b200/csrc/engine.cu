@@ -247,6 +247,9 @@ struct flope_engine {
   int roi_axis_tab = 1;                          // Lanczos4: coefficient tables from a pre-kernel (0 = the producer warps compute them)
   unsigned int* d_roi_sched = nullptr;           // work counter of the streaming ROI kernels (self-resetting)
   int roi_dynamic = 1;                           // streaming ROI kernels claim items from the counter (0 = static round-robin)
+  float4* d_split_ws = nullptr;                  // split-K partial accumulators of the trunk launch (latency tiles)
+  int trunk_splitk = kMaxSplit;                  // most splits per tile (< 2: off)
+  int trunk_split_stages = 15;                   // stages that may split (bit s)
   uint32_t* d_flags = nullptr;                   // completion counters of all chains, zeroed at the start of every forward
   size_t flags_per_chain = 0;                    // counters reserved per chain (kMaxChain layers x position tiles at max_batch)
   bool small_tiles = true;                       // latency-oriented tiles when max_batch is too small to fill the SMs
@@ -706,6 +709,39 @@ int trunk_shape_mask(const flope_engine* e) {
   return (mask == 0 || mask == 8 || mask == 12 || mask == 14 || mask == 15) ? mask : -1;
 }
 
+// Split-K for a stage on latency tiles whose layers would occupy less than half of the CTA pairs (ConvChain::k_splits):
+// as many splits as keep every item of a layer in one round of the pairs, each a contiguous range of K groups with about
+// the same number of weight tiles.
+constexpr size_t kSplitWsPerStage = (size_t)74 * 2 * 16 * 128;          // float4s: 74 partial items of 2 x 128 rows x 64 channels
+void plan_splits(const flope_engine* e, int s, ConvLayer* const* Ls, ConvChain& c) {
+  c.k_splits = 1;
+  if (e->trunk_splitk < 2 || !((e->trunk_split_stages >> s) & 1) || !e->d_split_ws || Ls[0]->n_tile != 64 || Ls[0]->mt != 1) return;
+  const int pairs = std::min(74, e->num_sms / 2);
+  // decided on the engine's max_batch, not on this call's n: the K partition - hence the rounding - of a crop's result
+  // must not depend on how many crops came with it
+  const int n_work = (int)(((long long)e->max_batch * c.L[0].Hp * c.L[0].Wp + 255) / 256) * c.L[0].n_n_tiles;
+  int ks = std::min(std::min(kMaxSplit, e->trunk_splitk), pairs / std::max(1, n_work));
+  for (int l = 0; l < c.n_layers; ++l) ks = std::min(ks, c.L[l].n_groups);
+  // measured on the streaming configuration (8 crops): layer4 (16 tiles, 3-4 splits) 133.6 -> 126 us for the trunk launch;
+  // layer3 (28 tiles, 2 splits) costs 4 us instead - the store / wait / reload of the partials outweighs half a K loop
+  if (ks < 3 || (size_t)n_work * (ks - 1) * 2 * 16 * 128 > kSplitWsPerStage) return;
+  for (int l = 0; l < c.n_layers; ++l) {
+    const ConvParams& q = c.L[l];
+    int g = 0, taps = 0;
+    c.split_group[l][0] = 0; c.split_tap[l][0] = 0;
+    for (int sp = 1; sp < ks; ++sp) {
+      // advance to the group boundary nearest to sp / ks of the taps, leaving a group for every later split
+      const int target = q.taps_total * sp / ks;
+      do { taps += q.group_ntaps[g]; ++g; } while (taps < target && g < q.n_groups - (ks - sp));
+      c.split_group[l][sp] = (unsigned char)g; c.split_tap[l][sp] = (unsigned short)taps;
+    }
+    c.split_group[l][ks] = (unsigned char)q.n_groups; c.split_tap[l][ks] = (unsigned short)q.taps_total;
+  }
+  c.k_splits = ks;
+  c.split_flags = c.flags + (size_t)c.n_layers * c.n_m_tiles;
+  c.split_ws = e->d_split_ws + (size_t)s * kSplitWsPerStage;
+}
+
 int run_trunk(flope_engine* e, int n, cudaStream_t st) {
   ProfScope ps(e, "conv:layer1-4 (one launch, 16 convs)", st);
   TrunkParams tp;                                 // ~11 KB of kernel arguments
@@ -717,7 +753,8 @@ int run_trunk(flope_engine* e, int n, cudaStream_t st) {
     for (int i = 0; i < kMaxChain; ++i) Ls[i] = &e->layers[e->chains[s][i]];
     if ((rc = build_chain(e, Ls, kMaxChain, n, e->d_flags + s * e->flags_per_chain, tp.st[s]))) return rc;
     tp.tile_pos[s] = Ls[0]->mt * 256;
-    items += (long long)tp.st[s].n_layers * tp.st[s].L[0].n_work;
+    plan_splits(e, s, Ls, tp.st[s]);
+    items += (long long)tp.st[s].n_layers * tp.st[s].L[0].n_work * std::max(1, tp.st[s].k_splits);
   }
   const size_t smem = trunk_smem(e);
   dim3 grid((unsigned)(2 * std::min<long long>(items, e->num_sms / 2)));
@@ -1023,10 +1060,11 @@ int flope_engine_create(flope_engine** out, int device, int max_batch, int crop_
     size_t per = 0;
     for (const auto& ch : e->chains) {
       const ConvParams& p = e->layers[ch[0]].p;
-      per = std::max(per, kChainHeader + (size_t)kMaxChain * ((size_t)e->max_batch * p.Hp * p.Wp / 128 + 2));
+      per = std::max(per, kChainHeader + (size_t)kMaxChain * ((size_t)e->max_batch * p.Hp * p.Wp / 128 + 2) + (size_t)kMaxChain * 128);   // + split-K counters
     }
     e->flags_per_chain = per;
     if (per) CUDA_TRY(cudaMalloc(&e->d_flags, e->chains.size() * per * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&e->d_split_ws, kTrunkStages * kSplitWsPerStage * sizeof(float4)));     // 19 MB: split-K partials of the latency tiles
   }
   CUDA_TRY(cudaDeviceSynchronize());
   *out = guard.release();
@@ -1042,6 +1080,7 @@ void flope_engine_destroy(flope_engine* e) {
   for (ConvLayer& L : e->layers) { cudaFree(L.d_w); cudaFree(L.d_bias); }
   cudaFree(e->stem_pool.d_w); cudaFree(e->stem_pool.d_bias);
   cudaFree(e->d_flags);
+  cudaFree(e->d_split_ws);
   cudaFree(e->d_roi_sched);
   cudaFree(e->d_roi_tab);
   cudaFree(e->d_stamps);
@@ -1400,6 +1439,8 @@ int flope_engine_set_schedule(flope_engine* e, int schedule) {
 int flope_debug_set(flope_engine* e, const char* key, int value) {
   if (!e || !key) return fail(FLOPE_EINVAL, "NULL argument");
   if (!std::strcmp(key, "use_graph")) { e->use_graph = value != 0; return FLOPE_OK; }
+  if (!std::strcmp(key, "trunk_splitk")) { e->trunk_splitk = value == 1 ? kMaxSplit : value; drop_graphs(e); return FLOPE_OK; }   // 0: off, 1: default
+  if (!std::strcmp(key, "trunk_split_stages")) { e->trunk_split_stages = value; drop_graphs(e); return FLOPE_OK; }
   if (!std::strcmp(key, "roi_stream")) { e->roi_stream = value; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_item_auto")) { e->roi_item_auto = value; return FLOPE_OK; }
   if (!std::strcmp(key, "roi_item_floor")) { e->roi_item_floor = std::max(1, value); return FLOPE_OK; }

@@ -57,7 +57,7 @@ struct TrunkRole {
   uint32_t a_par = 0, b_par = 0;       // per-slot parity of completed uses of the role's side of the rings
 };
 
-template <int N_TILE, int MT>
+template <int N_TILE, int MT, bool SPLIT = false>
 struct TrunkStage {
   static constexpr int KP = 4, KC8 = 8;
   static constexpr int TM = MT * 128;
@@ -68,6 +68,25 @@ struct TrunkStage {
   static constexpr int TILE_POS = 2 * TM;
   static constexpr uint32_t b_tile_bytes = (uint32_t)KC8 * NB_ROWS * 16u;
   static_assert(N_TILE * MT <= ACC_COLS, "a tile's accumulators fit one 256-column stage");
+  static_assert(!SPLIT || MT == 1, "split-K is for the latency tiles");
+
+  // Work item g of a stage -> (layer, tile, split) and the K-group range / first weight tile of the split.
+  struct Item { int l, w, sp, ks, gi0, gi1, tap0; };
+  static __device__ __forceinline__ int items_per_layer(const ConvChain& ch) {
+    return ch.L[0].n_work * (SPLIT && ch.k_splits > 1 ? ch.k_splits : 1);
+  }
+  static __device__ __forceinline__ Item decode(const ConvChain& ch, int g) {
+    Item it;
+    it.ks = SPLIT && ch.k_splits > 1 ? ch.k_splits : 1;
+    const int per_layer = ch.L[0].n_work * it.ks;
+    it.l = g / per_layer;
+    const int r = g - it.l * per_layer;
+    it.w = r / it.ks;
+    it.sp = r - it.w * it.ks;
+    it.gi0 = 0; it.gi1 = ch.L[it.l].n_groups; it.tap0 = 0;
+    if (SPLIT && it.ks > 1) { it.gi0 = ch.split_group[it.l][it.sp]; it.gi1 = ch.split_group[it.l][it.sp + 1]; it.tap0 = ch.split_tap[it.l][it.sp]; }
+    return it;
+  }
 
   // The rings of a stage start behind ITS bias block (kMaxChain x Cout floats), exactly as conv_igemm.cuh lays a chain
   // out, so the launch needs no more shared memory than the largest stage.  A later stage's larger bias block grows
@@ -88,7 +107,7 @@ struct TrunkStage {
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t a_ring_addr = ring_addr(ch, c);
     const uint32_t b_ring_addr = a_ring_addr + (uint32_t)p.n_a_slots * a_slot_bytes;
-    const int total = ch.n_layers * p.n_work;
+    const int total = ch.n_layers * items_per_layer(ch);
     const int img = p.Hp * p.Wp;
     int a_slot = 0, b_slot = 0;
     bool drained = prev == nullptr;
@@ -102,7 +121,8 @@ struct TrunkStage {
         for (int i = 0; i < kMaxBSlots; ++i) mbar_wait(&c.b_empty[i], ((s.b_par >> i) & 1u) ^ 1u);
         drained = true;
       }
-      const int l = g / p.n_work, w = g - l * p.n_work;
+      const Item it = decode(ch, g);
+      const int l = it.l, w = it.w;
       const ConvParams& q = ch.L[l];
       const int m = w / p.n_n_tiles;
       const int tile_start = m * TILE_POS + (int)c.rank * TM;
@@ -134,8 +154,8 @@ struct TrunkStage {
         }
       }
       const int n_tile = w % p.n_n_tiles;
-      const __nv_bfloat16* wtile = q.wgt + ((size_t)n_tile * q.taps_total * 2 + c.rank) * (b_tile_bytes / 2);
-      for (int gi = 0; gi < q.n_groups; ++gi) {
+      const __nv_bfloat16* wtile = q.wgt + (((size_t)n_tile * q.taps_total + it.tap0) * 2 + c.rank) * (b_tile_bytes / 2);
+      for (int gi = it.gi0; gi < it.gi1; ++gi) {
         mbar_wait(&c.a_empty[a_slot], ((s.a_par >> a_slot) & 1u) ^ 1u);
         mbar_expect_tx_if(leader, &c.a_full[a_slot], a_slot_bytes);
         const uint32_t a_dst = a_ring_addr + a_slot * a_slot_bytes;
@@ -167,13 +187,14 @@ struct TrunkStage {
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t a_full_remote = mapa_u32(smem_u32(c.a_full), 0);
     const uint32_t b_full_remote = mapa_u32(smem_u32(c.b_full), 0);
-    const int total = ch.n_layers * p.n_work;
+    const int total = ch.n_layers * items_per_layer(ch);
     int a_slot = 0, b_slot = 0;
     for (;; ++s.k) {
       const int g = c.first_work + s.k * c.work_stride - item_base;
       if (g >= total) break;
-      const ConvParams& q = ch.L[g / p.n_work];
-      for (int gi = 0; gi < q.n_groups; ++gi) {
+      const Item it = decode(ch, g);
+      const ConvParams& q = ch.L[it.l];
+      for (int gi = it.gi0; gi < it.gi1; ++gi) {
         mbar_wait(&c.a_full[a_slot], (s.a_par >> a_slot) & 1u);
         mbar_arrive_remote_if(leader, a_full_remote + a_slot * 8);
         s.a_par ^= 1u << a_slot;
@@ -204,22 +225,23 @@ struct TrunkStage {
     constexpr uint32_t b_kstep = 2u * NB_ROWS;
     const uint32_t a_slot_units = a_slot_bytes >> 4;
     constexpr uint32_t b_tile_units = b_tile_bytes >> 4;
-    const int total = ch.n_layers * p.n_work;
+    const int total = ch.n_layers * items_per_layer(ch);
     int a_slot = 0, b_slot = 0;
     for (;; ++s.k) {
       const int g = c.first_work + s.k * c.work_stride - item_base;
       if (g >= total) break;
-      const ConvParams& q = ch.L[g / p.n_work];
+      const Item it = decode(ch, g);
+      const ConvParams& q = ch.L[it.l];
       const uint32_t stage = s.it & 1;
       mbar_wait(&c.acc_empty[stage], ((s.it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t acc = c.tmem_base + stage * ACC_COLS;
       uint32_t accumulate = 0;
-      for (int gi = 0; gi < q.n_groups; ++gi) {
+      for (int gi = it.gi0; gi < it.gi1; ++gi) {
         mbar_wait(&c.a_full[a_slot], (s.a_par >> a_slot) & 1u);
         s.a_par ^= 1u << a_slot;
         const uint32_t a_grp = a_lo0 + a_slot * a_slot_units;
-        const bool last_group = gi == q.n_groups - 1;
+        const bool last_group = gi == it.gi1 - 1;
         const int tofs = q.group_tapofs[gi];
         const int ntaps = q.group_ntaps[gi];
         for (int t = 0; t < ntaps; ++t) {
@@ -258,7 +280,7 @@ struct TrunkStage {
     const int img = p.Hp * p.Wp;
     const int lane = c.lane;
     const uint32_t acc_empty_remote = mapa_u32(smem_u32(c.acc_empty), 0);
-    const int total = ch.n_layers * p.n_work;
+    const int total = ch.n_layers * items_per_layer(ch);
     // this stage's folded-BN biases: every epilogue warp is done with the previous stage's before they are replaced
     asm volatile("bar.sync 6, %0;" ::"n"(kEpiWarps * 32) : "memory");
     for (int i = (int)threadIdx.x - 64; i < ch.n_layers * p.Cout; i += kEpiWarps * 32) c.s_bias[i] = ch.L[i / p.Cout].bias[i % p.Cout];
@@ -266,7 +288,8 @@ struct TrunkStage {
     for (;; ++s.k) {
       const int g = c.first_work + s.k * c.work_stride - item_base;
       if (g >= total) break;
-      const int l = g / p.n_work, w = g - l * p.n_work;
+      const Item it = decode(ch, g);
+      const int l = it.l, w = it.w;
       const ConvParams& q = ch.L[l];
       const float* bias_l = c.s_bias + l * p.Cout;
       const uint32_t stage = s.it & 1;
@@ -275,6 +298,44 @@ struct TrunkStage {
       const int cout_base = n_tile * N_TILE;
       const uint32_t acc = c.tmem_base + stage * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
       bool waited = false;
+      if (SPLIT && it.sp + 1 < it.ks) {
+        // a partial: the raw accumulators go to the workspace ([column quad][row]: a warp's 32 rows are contiguous)
+        float4* ws = ch.split_ws + ((((size_t)w * (it.ks - 1) + it.sp) * 2 + c.rank) * (N_TILE / 4)) * 128 + quarter * 32 + lane;
+#pragma unroll 1
+        for (int cc = sub; cc < NCHUNK; cc += NSUB) {
+          if (!waited) {
+            mbar_wait(&c.acc_full[stage], (s.it >> 1) & 1);
+            tc_fence_after();
+            waited = true;
+          }
+          uint32_t v32[32];
+          tmem_ld32(acc + (uint32_t)(cc * 32), v32);
+          tmem_ld_wait();
+          if (cc + NSUB >= NCHUNK) {
+            tc_fence_before();
+            __syncwarp();
+            mbar_arrive_remote_if(lane == 0 ? 1u : 0u, acc_empty_remote + stage * 8);
+          }
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            ws[(size_t)(cc * 8 + j4) * 128] = make_float4(__uint_as_float(v32[4 * j4]), __uint_as_float(v32[4 * j4 + 1]),
+                                                         __uint_as_float(v32[4 * j4 + 2]), __uint_as_float(v32[4 * j4 + 3]));
+        }
+        if (!waited) {
+          mbar_wait(&c.acc_full[stage], (s.it >> 1) & 1);
+          tc_fence_before();
+          __syncwarp();
+          mbar_arrive_remote_if(lane == 0 ? 1u : 0u, acc_empty_remote + stage * 8);
+        }
+        asm volatile("bar.sync 5, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (threadIdx.x == 64) {
+          __threadfence();
+          atomicAdd(ch.split_flags + (size_t)l * p.n_work + w, 1u);
+        }
+        ++s.it;
+        continue;
+      }
+      bool partials_ready = false;
       if (q.res_layer >= 0) {
         wait_tile_flag(ch.flags + (size_t)q.res_layer * ch.n_m_tiles + w / p.n_n_tiles, ch.expected, ch.fail, ch.host_err);
         __syncwarp();
@@ -308,6 +369,26 @@ struct TrunkStage {
           tc_fence_before();
           __syncwarp();
           mbar_arrive_remote_if(lane == 0 ? 1u : 0u, acc_empty_remote + stage * 8);
+        }
+        if (SPLIT && it.ks > 1) {
+          if (!partials_ready) {
+            wait_tile_flag(ch.split_flags + (size_t)l * p.n_work + w, 2u * (uint32_t)(it.ks - 1), ch.fail, ch.host_err);
+            __syncwarp();
+            partials_ready = true;
+          }
+          if (valid) {
+            for (int s2 = 0; s2 < it.ks - 1; ++s2) {       // index order: the sum does not depend on who finished first
+              const float4* ws = ch.split_ws + ((((size_t)w * (it.ks - 1) + s2) * 2 + c.rank) * (N_TILE / 4) + (c0 >> 2)) * 128 + quarter * 32 + lane;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 t = __ldcg(ws + (size_t)j4 * 128);
+                v32[4 * j4] = __float_as_uint(__uint_as_float(v32[4 * j4]) + t.x);
+                v32[4 * j4 + 1] = __float_as_uint(__uint_as_float(v32[4 * j4 + 1]) + t.y);
+                v32[4 * j4 + 2] = __float_as_uint(__uint_as_float(v32[4 * j4 + 2]) + t.z);
+                v32[4 * j4 + 3] = __float_as_uint(__uint_as_float(v32[4 * j4 + 3]) + t.w);
+              }
+            }
+          }
         }
         if (valid) {
           float v[32];
@@ -368,7 +449,7 @@ struct TrunkStage {
 // Stage shapes of ResNet-18 with the CTA-pair plan (engine.cu plan_conv): 64 channels -> 64x4, 128 -> 128x2, >= 256 -> 256x1;
 // a stage whose layers would be too few items at the engine's max_batch runs on the latency tiles 64x1 instead
 // (bit s of SMALL; small batches switch the late stages first: 0, 8, 12, 14, 15 are the masks that occur).
-template <int S, bool SMALL> struct TrunkShape { using type = TrunkStage<64, 1>; };
+template <int S, bool SMALL> struct TrunkShape { using type = TrunkStage<64, 1, true>; };
 template <> struct TrunkShape<0, false> { using type = TrunkStage<64, 4>; };
 template <> struct TrunkShape<1, false> { using type = TrunkStage<128, 2>; };
 template <> struct TrunkShape<2, false> { using type = TrunkStage<256, 1>; };
@@ -425,7 +506,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) trunk_chain_kernel(const __gr
 
   int base[kTrunkStages + 1];
   base[0] = 0;
-  for (int s = 0; s < kTrunkStages; ++s) base[s + 1] = base[s] + tp.st[s].n_layers * tp.st[s].L[0].n_work;
+  for (int s = 0; s < kTrunkStages; ++s)
+    base[s + 1] = base[s] + tp.st[s].n_layers * tp.st[s].L[0].n_work * (tp.st[s].k_splits > 1 ? tp.st[s].k_splits : 1);
   TrunkRole role;
   if (c.warp == 0) {
     St0::producer(tp.st[0], nullptr, 0, base[0], c, role);
