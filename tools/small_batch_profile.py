@@ -33,12 +33,15 @@ def prof(tag, reps=30):
     print(f"   sum {tot:.1f} us")
 
 
+for kv in filter(None, os.environ.get("FLOPE_SET", "").split(",")):
+    eng.debug_set(kv.split("=")[0], int(kv.split("=")[1]))
+    eng.load_state_dict(synth.random_state_dict(0))
 eng.debug_set("use_graph", 0)
 eng.debug_set("chain", 0)
 prof("per-layer launches")
 eng.debug_set("chain", 1)
 eng.debug_set("trunk_splitk", 0)
 prof("trunk launch, no split-K")
-for ks, stages in ((4, 15), (4, 8), (4, 4), (2, 8), (3, 8), (2, 15)):
+for ks, stages in ((4, 15),):
     eng.debug_set("trunk_splitk", ks); eng.debug_set("trunk_split_stages", stages)
     prof(f"trunk launch, split-K up to {ks}, stage mask {stages}")
