@@ -115,6 +115,10 @@ struct ConvParams {
 // `flags` (a counter per position tile: n_n_tiles x CTAs of a pair parts), consumers wait on the three counters.
 constexpr int kMaxChain = 4;
 constexpr int kMaxSplit = 4;
+// trunk_chain_kernel, latency tiles: weight tiles (taps) per ring slot.  With 4 KB tiles and four short MMAs per tap the
+// per-slot handshakes (producer: empty -> expect -> copy; relay across the pair; issuer: full -> fence -> commit) pace the
+// K loop, not the tensor pipe (profiles/r2_notes.md): one barrier round per three taps.
+constexpr int kLatencyTapsPerSlot = 3;
 struct ConvChain {
   ConvParams L[kMaxChain];
   int n_layers;

@@ -467,9 +467,12 @@ int plan_conv(flope_engine* e, ConvLayer& L) {
     pool_smem = kPoolXchBytes;
   }
   const int halo = p.halo_before + p.halo_after;
+  // latency tiles: the trunk launch keeps kLatencyTapsPerSlot weight tiles in every ring slot (trunk_chain.cuh); the
+  // per-layer kernels use the first tile's worth of each slot
+  const int b_tiles_per_slot = (L.pair && L.n_tile == 64 && L.mt == 1 && L.kind != K_FC) ? kLatencyTapsPerSlot : 1;
   auto smem_of = [&](int n_a, int n_b) {
     return (size_t)1024 + (size_t)kMaxChain * L.cout * sizeof(float) + (size_t)n_a * p.kc8 * (span + halo) * 16 +
-           (size_t)n_b * p.kc8 * nb_rows * 16 + pool_smem;
+           (size_t)n_b * b_tiles_per_slot * p.kc8 * nb_rows * 16 + pool_smem;
   };
   // weight tiles are consumed every MT*kc8/2 MMAs, so several must be in flight to cover L2 latency;
   // halo tiles are consumed once per group: two or three slots are enough.  Rings run across tiles.

@@ -67,6 +67,8 @@ struct TrunkStage {
   static constexpr int NCHUNK = N_TILE / 32;
   static constexpr int TILE_POS = 2 * TM;
   static constexpr uint32_t b_tile_bytes = (uint32_t)KC8 * NB_ROWS * 16u;
+  static constexpr int TB = SPLIT ? kLatencyTapsPerSlot : 1;          // weight tiles per ring slot (one barrier round each)
+  static constexpr uint32_t b_slot_bytes = (uint32_t)TB * b_tile_bytes;
   static_assert(N_TILE * MT <= ACC_COLS, "a tile's accumulators fit one 256-column stage");
   static_assert(!SPLIT || MT == 1, "split-K is for the latency tiles");
 
@@ -169,11 +171,17 @@ struct TrunkStage {
         s.a_par ^= 1u << a_slot;
         if (++a_slot == p.n_a_slots) a_slot = 0;
         const int ntaps = q.group_ntaps[gi];
-        for (int t = 0; t < ntaps; ++t) {
+        for (int t = 0; t < ntaps; t += TB) {
+          const int nt = ntaps - t < TB ? ntaps - t : TB;
           mbar_wait(&c.b_empty[b_slot], ((s.b_par >> b_slot) & 1u) ^ 1u);
-          mbar_expect_tx_if(leader, &c.b_full[b_slot], b_tile_bytes);
-          bulk_g2s_if(leader, b_ring_addr + b_slot * b_tile_bytes, wtile, b_tile_bytes, &c.b_full[b_slot]);
-          wtile += 2 * (b_tile_bytes / 2);
+          mbar_expect_tx_if(leader, &c.b_full[b_slot], (uint32_t)nt * b_tile_bytes);
+#pragma unroll
+          for (int j = 0; j < TB; ++j) {
+            if (j < nt) {
+              bulk_g2s_if(leader, b_ring_addr + b_slot * b_slot_bytes + j * b_tile_bytes, wtile, b_tile_bytes, &c.b_full[b_slot]);
+              wtile += 2 * (b_tile_bytes / 2);
+            }
+          }
           s.b_par ^= 1u << b_slot;
           if (++b_slot == p.n_b_slots) b_slot = 0;
         }
@@ -199,7 +207,7 @@ struct TrunkStage {
         mbar_arrive_remote_if(leader, a_full_remote + a_slot * 8);
         s.a_par ^= 1u << a_slot;
         const int ntaps = q.group_ntaps[gi];
-        for (int t = 0; t < ntaps; ++t) {
+        for (int t = 0; t < ntaps; t += TB) {
           mbar_wait(&c.b_full[b_slot], (s.b_par >> b_slot) & 1u);
           mbar_arrive_remote_if(leader, b_full_remote + b_slot * 8);
           s.b_par ^= 1u << b_slot;
@@ -225,6 +233,7 @@ struct TrunkStage {
     constexpr uint32_t b_kstep = 2u * NB_ROWS;
     const uint32_t a_slot_units = a_slot_bytes >> 4;
     constexpr uint32_t b_tile_units = b_tile_bytes >> 4;
+    constexpr uint32_t b_slot_units = b_slot_bytes >> 4;
     const int total = ch.n_layers * items_per_layer(ch);
     int a_slot = 0, b_slot = 0;
     for (;; ++s.k) {
@@ -244,25 +253,31 @@ struct TrunkStage {
         const bool last_group = gi == it.gi1 - 1;
         const int tofs = q.group_tapofs[gi];
         const int ntaps = q.group_ntaps[gi];
-        for (int t = 0; t < ntaps; ++t) {
+        for (int t = 0; t < ntaps; t += TB) {
+          const int nt = ntaps - t < TB ? ntaps - t : TB;
           mbar_wait(&c.b_full[b_slot], (s.b_par >> b_slot) & 1u);
           s.b_par ^= 1u << b_slot;
           tc_fence_after();
-          const uint32_t a_tap = a_grp + (uint32_t)q.tap_shift[tofs + t];
-          const uint32_t b_tap = b_lo0 + b_slot * b_tile_units;
 #pragma unroll
-          for (int k = 0; k < KP; ++k) {
+          for (int j = 0; j < TB; ++j) {
+            if (j < nt) {
+              const uint32_t a_tap = a_grp + (uint32_t)q.tap_shift[tofs + t + j];
+              const uint32_t b_tap = b_lo0 + b_slot * b_slot_units + j * b_tile_units;
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              umma2_bf16_if(leader, acc + mt * N_TILE, a_tap + k * a_kstep + mt * 128u, desc_hi, b_tap + k * b_kstep, desc_hi,
-                            IDESC, k == 0 ? accumulate : 1u);
+              for (int k = 0; k < KP; ++k) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+                  umma2_bf16_if(leader, acc + mt * N_TILE, a_tap + k * a_kstep + mt * 128u, desc_hi, b_tap + k * b_kstep, desc_hi,
+                                IDESC, k == 0 ? accumulate : 1u);
+              }
+              accumulate = 1;
+            }
           }
           tc_commit2_if(leader, &c.b_empty[b_slot]);
-          if (t == ntaps - 1) {
+          if (t + nt == ntaps) {
             tc_commit2_if(leader, &c.a_empty[a_slot]);
             if (last_group) tc_commit2_if(leader, &c.acc_full[stage]);
           }
-          accumulate = 1;
           if (++b_slot == p.n_b_slots) b_slot = 0;
         }
         if (++a_slot == p.n_a_slots) a_slot = 0;
