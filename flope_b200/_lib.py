@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libflope_b200.so")
 
 INTERP_LINEAR, INTERP_LANCZOS4 = 0, 1
 OUT_F32_NCHW, OUT_ENGINE = 0, 1
+SCHED_PERSISTENT, SCHED_PER_LAYER, SCHED_DYNAMIC, SCHED_COOPERATIVE = 0, 1, 2, 3      # FLOPE_SCHED_* (include/flope_b200.h)
 
 SYMBOLS = [
     "flope_version", "flope_last_error", "flope_engine_create", "flope_engine_destroy",

@@ -116,3 +116,32 @@ def test_squarify_filter_property_vs_reference_arithmetic(L):
         assert np.array_equal(sq, want[want_keep].astype(np.int32))
 
     check()
+
+
+def test_python_constants_match_the_header():
+    """The ctypes layer repeats the header's enumerators; a missing or drifting one is an AttributeError (or worse, a
+    wrong schedule) in product code such as pipeline.EnginePool."""
+    import re
+    from flope_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "flope_b200.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(FLOPE_[A-Z0-9_]+)\s+(-?\d+)\b", hdr)}
+    for name in ("SCHED_PERSISTENT", "SCHED_PER_LAYER", "SCHED_DYNAMIC", "SCHED_COOPERATIVE"):
+        assert getattr(_lib, name) == defs["FLOPE_" + name], name
+    for name, key in (("INTERP_LINEAR", "FLOPE_INTERP_LINEAR"), ("INTERP_LANCZOS4", "FLOPE_INTERP_LANCZOS4"),
+                      ("OUT_F32_NCHW", "FLOPE_OUT_F32_NCHW"), ("OUT_ENGINE", "FLOPE_OUT_ENGINE")):
+        if key in defs:
+            assert getattr(_lib, name) == defs[key], name
+
+
+def test_every_lib_attribute_the_package_uses_exists():
+    """flope_b200/*.py only reaches for _lib names that _lib defines (catches a constant used before it was added)."""
+    import re
+    from flope_b200 import _lib
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "flope_b200")
+    missing = []
+    for fn in sorted(os.listdir(pkg)):
+        if fn.endswith(".py") and fn != "_lib.py":
+            for name in set(re.findall(r"\b_lib\.([A-Za-z_][A-Za-z0-9_]*)", open(os.path.join(pkg, fn)).read())):
+                if not hasattr(_lib, name):
+                    missing.append((fn, name))
+    assert not missing, missing

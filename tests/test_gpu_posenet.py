@@ -257,6 +257,32 @@ def test_staged_pool_matches_single_engine(cuda_lib, net):
         one.close()
 
 
+@pytest.mark.parametrize("kw", [{}, {"dynamic_chains": True}, {"cooperative_chains": True}])
+def test_overlapping_pool_matches_single_engine(cuda_lib, net, kw):
+    """EnginePool with engines meant to overlap (per-layer launches by default, or dynamic / cooperative stage chains via
+    flope_engine_set_schedule): several steps in flight on two streams, same bits as one engine."""
+    from flope_b200.pipeline import EnginePool
+    import inspect
+    if any(k not in inspect.signature(EnginePool.__init__).parameters for k in kw):
+        pytest.skip("EnginePool has no such option")
+    xs = [synth.mixed_crops(40, 224, seed=s).cuda() for s in (11, 12, 13)]
+    one = cuda_lib.Engine(0, max_batch=40, crop_hw=224)
+    pool = EnginePool("cuda:0", n_engines=2, max_batch=40, crop_hw=224, state_dict=net.state_dict(), **kw)
+    try:
+        one.load_state_dict(net.state_dict())
+        refs = [one.posenet_forward(x).clone() for x in xs]
+        outs = [torch.empty((40, 9), device="cuda") for _ in range(8)]
+        for i in range(8):
+            pool.submit(lambda e, k, i=i: e.posenet_forward(xs[i % 3], out=outs[i]))
+        pool.join()
+        torch.cuda.synchronize()
+        for i in range(8):
+            assert torch.equal(outs[i], refs[i % 3]), i
+    finally:
+        pool.close()
+        one.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("max_batch,n", [(8, 8), (8, 3), (32, 32), (64, 50), (120, 120)])
 def test_trunk_launch_small_batches_bitwise(cuda_lib, net, max_batch, n):
