@@ -23,7 +23,12 @@
 //     rows h0..h1 of crop range n0..n1 <- full-res rows 2*h0 .. 2*h1+1, a contiguous tile range.  The 1x1 projection
 //     (folded into conv2 as extra K) reads positions its own conv1 neighbours already waited for;
 //   * the epilogue warps re-stage the stage's folded-BN biases between two named barriers of their own; each stage's
-//     rings start right behind its own bias block.
+//     rings start right behind its own bias block;
+//   * latency tiles (TrunkStage<64, 1, true>: small max_batch, e.g. a streamed frame with 8 flowers) keep three weight
+//     tiles per ring slot - one barrier round per three taps for producer, relay and issuer - and may split K: a
+//     stage whose layers are at most a third of the CTA pairs deals every tile as k_splits items over disjoint K-group
+//     ranges; the first k_splits-1 store raw fp32 accumulators and count themselves in split_flags, the last adds them
+//     in index order and runs the epilogue (ConvChain::k_splits, engine.cu plan_splits).
 // Static dealing needs every CTA resident (grid <= SM count, one such launch on the device at a time) - the same
 // condition as the per-stage chains.  engine.cu enforces it: forwards that contain these launches pass a per-device
 // gate (an event chain under a host mutex), so two engines on two streams run their backbones one after the other;
